@@ -1,0 +1,150 @@
+"""TEST INFRASTRUCTURE: ctypes binding of oracle/libcg_oracle.so (cg_oracle.h)
+and a runner for oracle/_ref/ref_cg (the reference's own SolverConjugate built
+from /root/reference/src by oracle/ref/Makefile).  Never imported by the
+product package `aphros_b200`.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcg_oracle.so")
+REF_DIR = os.path.join(_HERE, "_ref")
+REF_CG = os.path.join(REF_DIR, "ref_cg")
+
+
+class _Desc(ctypes.Structure):
+    _fields_ = [
+        ("nx", ctypes.c_long), ("ny", ctypes.c_long), ("nz", ctypes.c_long),
+        ("periodic", ctypes.c_int * 3),
+        ("bsx", ctypes.c_long), ("bsy", ctypes.c_long), ("bsz", ctypes.c_long),
+        ("cell_volume", ctypes.c_double),
+        ("tol", ctypes.c_double),
+        ("miniter", ctypes.c_int), ("maxiter", ctypes.c_int), ("maxnorm", ctypes.c_int),
+    ]
+
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", _HERE, "libcg_oracle.so"], check=True,
+                   stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = ctypes.CDLL(LIB_PATH)
+        dp = ctypes.POINTER(ctypes.c_double)
+        for name in ("cg_oracle_conjugate", "cg_oracle_jacobi"):
+            f = getattr(_lib, name)
+            f.restype = ctypes.c_int
+            f.argtypes = [ctypes.POINTER(_Desc), dp, dp, dp, dp,
+                          ctypes.POINTER(ctypes.c_int), dp]
+        _lib.cg_oracle_apply.restype = ctypes.c_int
+        _lib.cg_oracle_apply.argtypes = [ctypes.POINTER(_Desc), dp, dp, dp]
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if a is not None else None
+
+
+def _desc(shape, periodic, block, cell_volume, tol, miniter, maxiter, maxnorm):
+    nz, ny, nx = shape
+    d = _Desc()
+    d.nx, d.ny, d.nz = nx, ny, nz
+    d.periodic[:] = [int(bool(p)) for p in periodic]
+    b = block if block is not None else (0, 0, 0)
+    if isinstance(b, int):
+        b = (b, b, b)
+    d.bsx, d.bsy, d.bsz = b
+    d.cell_volume = cell_volume
+    d.tol, d.miniter, d.maxiter, d.maxnorm = tol, miniter, maxiter, int(maxnorm)
+    return d
+
+
+def solve(system, x0=None, *, periodic=(True, True, True), cell_volume=None, tol=0.0,
+          miniter=0, maxiter=100, maxnorm=False, block=None, method="conjugate"):
+    """Run the C restatement.  system: (nz,ny,nx,8).  Returns (x, iter, residual, history)."""
+    system = np.ascontiguousarray(system, dtype=np.float64)
+    shape = system.shape[:3]
+    if cell_volume is None:
+        cell_volume = (1.0 / max(shape)) ** 3
+    x0c = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+    x = np.empty(shape, dtype=np.float64)
+    hist = np.zeros(maxiter + 2, dtype=np.float64)
+    res = ctypes.c_double()
+    it = ctypes.c_int()
+    d = _desc(shape, periodic, block, cell_volume, tol, miniter, maxiter, maxnorm)
+    fn = lib().cg_oracle_conjugate if method == "conjugate" else lib().cg_oracle_jacobi
+    rc = fn(ctypes.byref(d), _dp(system), _dp(x0c), _dp(x), ctypes.byref(res),
+            ctypes.byref(it), _dp(hist))
+    if rc != 0:
+        raise MemoryError("cg_oracle: allocation failed")
+    return x, it.value, res.value, hist[:it.value].copy()
+
+
+def apply(system, v, *, periodic=(True, True, True)):
+    system = np.ascontiguousarray(system, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.empty_like(v)
+    d = _desc(system.shape[:3], periodic, None, 1.0, 0.0, 0, 0, False)
+    lib().cg_oracle_apply(ctypes.byref(d), _dp(system), _dp(v), _dp(out))
+    return out
+
+
+def have_reference():
+    return os.path.exists(REF_CG)
+
+
+def solve_reference(system, x0=None, *, periodic=(True, True, True), tol=0.0, miniter=0,
+                    maxiter=100, maxnorm=False, block=None, solver="conjugate",
+                    plugin=None, threads=1, repeat=1, extra="", env=None, workdir=None):
+    """Run the reference's own solver (oracle/_ref/ref_cg).
+
+    Returns (x, iter, residual, seconds).  Mesh extent is 1 (h = 1/max(n)).
+    """
+    system = np.ascontiguousarray(system, dtype=np.float64)
+    nz, ny, nx = system.shape[:3]
+    b = block if block is not None else (nx, ny, nz)
+    if isinstance(b, int):
+        b = (b, b, b)
+    with tempfile.TemporaryDirectory(dir=workdir) as tmp:
+        fsys = os.path.join(tmp, "sys.f64")
+        system.tofile(fsys)
+        cmd = [REF_CG, "--nx", str(nx), "--ny", str(ny), "--nz", str(nz),
+               "--bsx", str(b[0]), "--bsy", str(b[1]), "--bsz", str(b[2]),
+               "--sys", fsys, "--out", os.path.join(tmp, "out"),
+               "--tol", repr(float(tol)), "--maxiter", str(maxiter), "--miniter", str(miniter),
+               "--maxnorm", str(int(maxnorm)),
+               "--px", str(int(periodic[0])), "--py", str(int(periodic[1])),
+               "--pz", str(int(periodic[2])), "--solver", solver, "--repeat", str(repeat)]
+        if x0 is not None:
+            fx0 = os.path.join(tmp, "x0.f64")
+            np.ascontiguousarray(x0, dtype=np.float64).tofile(fx0)
+            cmd += ["--x0", fx0]
+        if plugin:
+            cmd += ["--plugin", plugin]
+        if extra:
+            cmd += ["--extra", extra]
+        e = dict(os.environ)
+        e["OMP_NUM_THREADS"] = str(threads)
+        if env:
+            e.update(env)
+        p = subprocess.run(cmd, cwd=tmp, env=e, capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError("ref_cg failed:\n" + p.stdout + p.stderr)
+        x = np.fromfile(os.path.join(tmp, "out.x"), dtype=np.float64).reshape(nz, ny, nx)
+        with open(os.path.join(tmp, "out.info")) as f:
+            it, res, sec = f.read().split()
+    return x, int(it), float(res), float(sec)
