@@ -1,0 +1,926 @@
+// libaphcg.so: C ABI (include/aphcg.h) and host-side driver of the CG solver.
+//
+// Mirrors linear::Solver<M>::Solve of the reference (src/linear/linear.h:15-57):
+// one call uploads the 8-coefficient rows and the initial guess, runs the
+// device-resident loop (cg_kernels.cu) until the reference's exit rule fires
+// (src/linear/linear.ipp:102-113) and downloads the solution.  There is no CPU
+// fallback: without a usable CUDA device every compute entry point fails.
+#include "../../include/aphcg.h"
+
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cg_launch.h"
+#include "cg_types.h"
+#include "nccl_dl.h"
+
+using namespace acg;
+
+namespace {
+
+thread_local std::string g_error;
+
+int Fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return Fail(APHCG_ERR_CUDA, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call,    \
+                  cudaGetErrorString(e_));                                              \
+  } while (0)
+
+#define NK(call)                                                                        \
+  do {                                                                                  \
+    ncclResult_t e_ = (call);                                                           \
+    if (e_ != ncclSuccess)                                                              \
+      return Fail(APHCG_ERR_COMM, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call,    \
+                  Nccl().GetErrorString(e_));                                           \
+  } while (0)
+
+struct IpcBlob {  // <= APHCG_IPC_BYTES
+  cudaIpcMemHandle_t handle;  // 64 bytes
+  int64_t ptotal, pz, poff, nzl;
+  int32_t rank, pid;
+  uint64_t base;  // device pointer (valid in the exporting process only)
+};
+static_assert(sizeof(IpcBlob) <= APHCG_IPC_BYTES, "blob too large");
+static_assert(sizeof(ncclUniqueId) <= APHCG_UNIQUE_ID_BYTES, "id too large");
+
+constexpr size_t kStageBytes = size_t(128) << 20;
+constexpr int kChunkIters = 16;
+
+}  // namespace
+
+struct aphcg {
+  aphcg_desc desc{};
+  Geom g{};
+  int vx = 1;
+  bool single = true;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  double* coef[7] = {};
+  double* rhs = nullptr;
+  double* u = nullptr;
+  double* ap = nullptr;
+  double* slab = nullptr;  // r | p0 | p1, padded
+  CgState* st = nullptr;
+  CgState* h_st = nullptr;  // pinned
+  double* history = nullptr;
+  double* partials = nullptr;
+  double* partials2 = nullptr;
+  unsigned nslots = 0;
+  int hist_cap = 0;
+  double* stage[2] = {};
+  cudaEvent_t stage_free[2] = {}, stage_ready[2] = {};
+  cudaEvent_t ev[4] = {};
+  DevPtrs d{};
+  bool have_system = false, have_guess = false;
+  // loop graph
+  cudaGraphExec_t gexec = nullptr;
+  cudaGraphExec_t gexec_jacobi = nullptr;
+  bool use_graph = true;
+  bool use_tma = false;
+  TmaPlan* tma = nullptr;
+  // comm
+  ncclComm_t comm = nullptr;
+  void* peer_lo = nullptr;
+  void* peer_hi = nullptr;
+  bool peer_lo_opened = false, peer_hi_opened = false;
+  bool connected = false;
+  int64_t launches = 0;
+  int last_iter = 0;
+};
+
+namespace {
+
+int SetDevice(aphcg_t* h) {
+  CK(cudaSetDevice(h->desc.device));
+  return 0;
+}
+
+void InvalidateGraphs(aphcg_t* h) {
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  if (h->gexec_jacobi) cudaGraphExecDestroy(h->gexec_jacobi);
+  h->gexec = nullptr;
+  h->gexec_jacobi = nullptr;
+}
+
+void FillDevPtrs(aphcg_t* h) {
+  DevPtrs& d = h->d;
+  for (int q = 0; q < 7; ++q) d.a[q] = h->coef[q];
+  d.rhs = h->rhs;
+  d.u = h->u;
+  d.ap = h->ap;
+  d.r = h->slab;
+  d.p[0] = h->slab + h->g.ptotal;
+  d.p[1] = h->slab + 2 * h->g.ptotal;
+  d.st = h->st;
+  d.history = h->history;
+  d.partials = h->partials;
+  d.partials2 = h->partials2;
+  d.r_lo_dst = d.r_hi_dst = nullptr;
+  d.p_lo_dst[0] = d.p_lo_dst[1] = d.p_hi_dst[0] = d.p_hi_dst[1] = nullptr;
+}
+
+// z images when the slab wraps onto itself (one rank, periodic z)
+void SelfConnect(aphcg_t* h) {
+  const Geom& g = h->g;
+  DevPtrs& d = h->d;
+  if (h->desc.nranks == 1 && h->desc.periodic[2]) {
+    double* f[3] = {d.r, d.p[0], d.p[1]};
+    double* lo[3];
+    double* hi[3];
+    for (int m = 0; m < 3; ++m) {
+      lo[m] = f[m] + g.poff + (int64_t)g.nzl * g.pz;  // bottom plane -> top ghost
+      hi[m] = f[m] + g.poff - g.pz;                    // top plane -> bottom ghost
+    }
+    d.r_lo_dst = lo[0];
+    d.r_hi_dst = hi[0];
+    d.p_lo_dst[0] = lo[1];
+    d.p_hi_dst[0] = hi[1];
+    d.p_lo_dst[1] = lo[2];
+    d.p_hi_dst[1] = hi[2];
+  }
+}
+
+int AllReduce(aphcg_t* h, double* p, ncclRedOp_t op) {
+  NK(Nccl().AllReduce(p, p, 1, ncclDouble, op, h->comm, h->stream));
+  return 0;
+}
+
+// One CG iteration enqueued on h->stream.
+int EnqueueIteration(aphcg_t* h) {
+  if (h->use_tma) {
+    launch_dir_spmv_tma(h->tma, h->g, h->d, h->single, h->stream);
+  } else {
+    launch_dir_spmv_plain(h->g, h->d, h->vx, h->single, h->stream);
+  }
+  if (!h->single) {
+    if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
+    launch_finish_dir(h->d, h->stream);
+  }
+  launch_update(h->g, h->d, h->vx, h->single, h->stream);
+  if (!h->single) {
+    if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
+    if (h->desc.flags & APHCG_MAXNORM) {
+      if (int rc = AllReduce(h, &h->st->loc_max, ncclMax)) return rc;
+    }
+    launch_finish_upd(h->d, h->stream);
+  }
+  return 0;
+}
+
+int EnqueueJacobiIteration(aphcg_t* h) {
+  launch_jacobi(h->g, h->d, h->vx, h->single, h->stream);
+  if (!h->single) {
+    if (int rc = AllReduce(h, &h->st->loc_max, ncclMax)) return rc;
+    launch_finish_jacobi(h->d, h->stream);
+  }
+  return 0;
+}
+
+int LaunchesPerIter(const aphcg_t* h) { return h->single ? 2 : 4; }
+
+int BuildGraph(aphcg_t* h, bool jacobi, cudaGraphExec_t* out) {
+  cudaGraph_t graph = nullptr;
+  CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = 0;
+  for (int i = 0; i < kChunkIters && rc == 0; ++i) {
+    rc = jacobi ? EnqueueJacobiIteration(h) : EnqueueIteration(h);
+  }
+  cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return Fail(APHCG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(out, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess)
+    return Fail(APHCG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// cross-rank barrier on the stream (orders peer-memory writes before reads)
+int StreamBarrier(aphcg_t* h) {
+  if (h->single) return 0;
+  return AllReduce(h, &h->st->loc_max, ncclMax);
+}
+
+int CheckLayout(const aphcg_t* h, const aphcg_layout* l, aphcg_layout* out) {
+  if (l) {
+    *out = *l;
+    if (l->stride_y < h->g.nx || l->stride_z < l->stride_y * (int64_t)h->g.ny || l->offset < 0)
+      return Fail(APHCG_ERR_ARG, "bad layout: offset=%lld stride_y=%lld stride_z=%lld",
+                  (long long)l->offset, (long long)l->stride_y, (long long)l->stride_z);
+  } else {
+    out->offset = 0;
+    out->stride_y = h->g.nx;
+    out->stride_z = (int64_t)h->g.nx * h->g.ny;
+  }
+  return 0;
+}
+
+bool IsCompact(const aphcg_t* h, const aphcg_layout& l) {
+  return l.stride_y == h->g.nx && l.stride_z == (int64_t)h->g.nx * h->g.ny;
+}
+
+// Copies planes [k0,k0+nk) of a laid-out host/device array of `elem`-byte cells
+// into a compact device/host chunk (or back), on stream s.
+int CopyPlanes(const aphcg_t* h, void* dst, const void* src, const aphcg_layout& l, bool src_laid,
+               int k0, int nk, size_t elem, cudaMemcpyKind kind, cudaStream_t s) {
+  const Geom& g = h->g;
+  const size_t row = (size_t)g.nx * elem;
+  if (IsCompact(h, l)) {
+    const size_t off = ((size_t)l.offset + (size_t)k0 * l.stride_z) * elem;
+    const size_t bytes = (size_t)nk * g.ny * row;
+    if (src_laid) {
+      CK(cudaMemcpyAsync(dst, (const char*)src + off, bytes, kind, s));
+    } else {
+      CK(cudaMemcpyAsync((char*)dst + off, src, bytes, kind, s));
+    }
+    return 0;
+  }
+  for (int k = 0; k < nk; ++k) {
+    const size_t off = ((size_t)l.offset + (size_t)(k0 + k) * l.stride_z) * elem;
+    const size_t coff = (size_t)k * g.ny * row;
+    if (src_laid) {
+      CK(cudaMemcpy2DAsync((char*)dst + coff, row, (const char*)src + off, l.stride_y * elem, row,
+                           g.ny, kind, s));
+    } else {
+      CK(cudaMemcpy2DAsync((char*)dst + off, l.stride_y * elem, (const char*)src + coff, row, row,
+                           g.ny, kind, s));
+    }
+  }
+  return 0;
+}
+
+int EnsureStage(aphcg_t* h) {
+  for (int b = 0; b < 2; ++b) {
+    if (!h->stage[b]) {
+      CK(cudaMalloc(&h->stage[b], kStageBytes));
+      CK(cudaEventCreateWithFlags(&h->stage_free[b], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->stage_ready[b], cudaEventDisableTiming));
+    }
+  }
+  return 0;
+}
+
+int WriteState(aphcg_t* h, const aphcg_conf* conf) {
+  CgState s{};
+  s.tol = conf->tol;
+  s.miniter = conf->miniter;
+  s.maxiter = conf->maxiter;
+  s.maxnorm = (h->desc.flags & APHCG_MAXNORM) ? 1 : 0;
+  s.cell_volume = h->desc.cell_volume;
+  s.hist_cap = h->hist_cap;
+  *h->h_st = s;
+  CK(cudaMemcpyAsync(h->st, h->h_st, sizeof(CgState), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+int EnsureHistory(aphcg_t* h, int maxiter) {
+  const int need = std::max(maxiter + 2, 16);
+  if (need > h->hist_cap) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->history) CK(cudaFree(h->history));
+    CK(cudaMalloc(&h->history, sizeof(double) * (size_t)need));
+    h->hist_cap = need;
+    h->d.history = h->history;
+    InvalidateGraphs(h);
+  }
+  return 0;
+}
+
+// Replays iterations until the device-side exit rule fires.
+int RunLoop(aphcg_t* h, bool jacobi, const aphcg_conf* conf) {
+  cudaGraphExec_t* gx = jacobi ? &h->gexec_jacobi : &h->gexec;
+  if (h->use_graph && !*gx) {
+    if (int rc = BuildGraph(h, jacobi, gx)) return rc;
+  }
+  // Upper bound on useful iterations: maxiter+1 (linear.ipp:110-113) or miniter.
+  const long limit = std::max<long>((long)conf->maxiter + 1, (long)conf->miniter);
+  long enq = 0;
+  for (;;) {
+    if (h->use_graph) {
+      CK(cudaGraphLaunch(*gx, h->stream));
+    } else {
+      for (int i = 0; i < kChunkIters; ++i) {
+        if (int rc = jacobi ? EnqueueJacobiIteration(h) : EnqueueIteration(h)) return rc;
+      }
+    }
+    enq += kChunkIters;
+    // poll the exit flag only when it can have fired: always with a tolerance,
+    // otherwise once the iteration limit is covered
+    if (conf->tol > 0 || enq >= limit) {
+      CK(cudaMemcpyAsync(h->h_st, h->st, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (h->h_st->done) break;
+      if (enq > limit + kChunkIters)
+        return Fail(APHCG_ERR_STATE, "loop did not terminate (iter=%d)", h->h_st->iter);
+    }
+  }
+  h->launches += (int64_t)h->h_st->iter * (jacobi ? (h->single ? 1 : 2) : LaunchesPerIter(h));
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================
+extern "C" {
+
+const char* aphcg_last_error(void) { return g_error.c_str(); }
+int aphcg_version(void) { return APHCG_VERSION; }
+
+int aphcg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int aphcg_host_alloc(void** out, uint64_t bytes) {
+  if (!out) return Fail(APHCG_ERR_ARG, "null out");
+  CK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return 0;
+}
+int aphcg_host_free(void* p) {
+  CK(cudaFreeHost(p));
+  return 0;
+}
+
+int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
+  if (!out || !desc) return Fail(APHCG_ERR_ARG, "null argument");
+  *out = nullptr;
+  const aphcg_desc& ds = *desc;
+  if (ds.nx < 1 || ds.ny < 1 || ds.nz < 1 || ds.nx > (1 << 20) || ds.ny > (1 << 20) ||
+      ds.nz > (1 << 20))
+    return Fail(APHCG_ERR_ARG, "bad mesh size %lld x %lld x %lld", (long long)ds.nx,
+                (long long)ds.ny, (long long)ds.nz);
+  if (ds.nranks < 1 || ds.rank < 0 || ds.rank >= ds.nranks)
+    return Fail(APHCG_ERR_ARG, "bad rank %d of %d", ds.rank, ds.nranks);
+  if (ds.nz_local < 1 || ds.z0 < 0 || ds.z0 + ds.nz_local > ds.nz)
+    return Fail(APHCG_ERR_ARG, "bad slab z0=%lld nz_local=%lld of nz=%lld", (long long)ds.z0,
+                (long long)ds.nz_local, (long long)ds.nz);
+  if (ds.nranks == 1 && (ds.z0 != 0 || ds.nz_local != ds.nz))
+    return Fail(APHCG_ERR_ARG, "one rank must own the whole domain");
+  if (!(ds.cell_volume > 0)) return Fail(APHCG_ERR_ARG, "cell_volume must be positive");
+  int ndev = aphcg_device_count();
+  if (ndev <= 0)
+    return Fail(APHCG_ERR_CUDA, "no CUDA device available (aphcg has no CPU fallback)");
+  if (ds.device < 0 || ds.device >= ndev)
+    return Fail(APHCG_ERR_ARG, "device %d out of range (%d devices)", ds.device, ndev);
+
+  aphcg_t* h = new aphcg();
+  h->desc = ds;
+  h->single = (ds.nranks == 1);
+  Geom& g = h->g;
+  g.nx = (int)ds.nx;
+  g.ny = (int)ds.ny;
+  g.nzl = (int)ds.nz_local;
+  g.per_x = ds.periodic[0] != 0;
+  g.per_y = ds.periodic[1] != 0;
+  g.cy = g.nx;
+  g.cz = (int64_t)g.nx * g.ny;
+  g.ncell = g.cz * g.nzl;
+  g.py = ((int64_t)kGhostX + g.nx + 1 + 15) / 16 * 16;
+  g.pz = g.py * (g.ny + 2);
+  g.poff = kGhostX + g.py + g.pz;
+  g.ptotal = g.pz * (g.nzl + 2);
+  h->vx = (g.nx % 2 == 0) ? 2 : 1;
+  h->use_graph = !(ds.flags & APHCG_NO_GRAPH);
+
+  auto cleanup = [&](int rc) {
+    aphcg_destroy(h);
+    return rc;
+  };
+#define CKC(call)                                                                      \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return cleanup(Fail(APHCG_ERR_CUDA, "%s:%d: %s failed: %s", __FILE__, __LINE__,  \
+                          #call, cudaGetErrorString(e_)));                             \
+  } while (0)
+  CKC(cudaSetDevice(ds.device));
+  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CKC(cudaEventCreate(&e));
+  const size_t nb = sizeof(double) * (size_t)g.ncell;
+  for (int q = 0; q < 7; ++q) CKC(cudaMalloc(&h->coef[q], nb));
+  CKC(cudaMalloc(&h->rhs, nb));
+  CKC(cudaMalloc(&h->u, nb));
+  CKC(cudaMalloc(&h->ap, nb));
+  CKC(cudaMalloc(&h->slab, sizeof(double) * 3 * (size_t)g.ptotal));
+  CKC(cudaMemset(h->slab, 0, sizeof(double) * 3 * (size_t)g.ptotal));
+  CKC(cudaMalloc(&h->st, sizeof(CgState)));
+  CKC(cudaMemset(h->st, 0, sizeof(CgState)));
+  CKC(cudaHostAlloc(&h->h_st, sizeof(CgState), cudaHostAllocDefault));
+  h->nslots = std::max(tile_blocks(g, h->vx), 1u);
+  FillDevPtrs(h);
+  SelfConnect(h);
+  // TMA-staged kernel unless disabled or the geometry does not qualify
+  const char* env = getenv("APHCG_SPMV");
+  bool want_tma = !(ds.flags & APHCG_NO_TMA);
+  if (env && !strcmp(env, "plain")) want_tma = false;
+  if (want_tma) {
+    char err[256] = "";
+    h->tma = tma_plan_create(g, h->d, err, sizeof(err));
+    if (h->tma) {
+      h->use_tma = true;
+      h->nslots = std::max(h->nslots, tma_plan_blocks(h->tma));
+    } else if (env && !strcmp(env, "tma")) {
+      return cleanup(Fail(APHCG_ERR_CUDA, "TMA kernel requested but unavailable: %s", err));
+    }
+  }
+  CKC(cudaMalloc(&h->partials, sizeof(double) * h->nslots));
+  CKC(cudaMalloc(&h->partials2, sizeof(double) * h->nslots));
+  h->d.partials = h->partials;
+  h->d.partials2 = h->partials2;
+  h->hist_cap = 128;
+  CKC(cudaMalloc(&h->history, sizeof(double) * h->hist_cap));
+  h->d.history = h->history;
+  CKC(cudaDeviceSynchronize());
+#undef CKC
+  *out = h;
+  return 0;
+}
+
+int aphcg_destroy(aphcg_t* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->desc.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  InvalidateGraphs(h);
+  if (h->tma) tma_plan_destroy(h->tma);
+  if (h->comm) Nccl().CommDestroy(h->comm);
+  if (h->peer_lo_opened) cudaIpcCloseMemHandle(h->peer_lo);
+  if (h->peer_hi_opened) cudaIpcCloseMemHandle(h->peer_hi);
+  for (int q = 0; q < 7; ++q) cudaFree(h->coef[q]);
+  cudaFree(h->rhs);
+  cudaFree(h->u);
+  cudaFree(h->ap);
+  cudaFree(h->slab);
+  cudaFree(h->st);
+  cudaFree(h->history);
+  cudaFree(h->partials);
+  cudaFree(h->partials2);
+  if (h->h_st) cudaFreeHost(h->h_st);
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(h->stage[b]);
+    if (h->stage_free[b]) cudaEventDestroy(h->stage_free[b]);
+    if (h->stage_ready[b]) cudaEventDestroy(h->stage_ready[b]);
+  }
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaGetLastError();
+  delete h;
+  return 0;
+}
+
+// ---- uploads -------------------------------------------------------------------
+int aphcg_upload_system(aphcg_t* h, const double* system, const aphcg_layout* layout) {
+  if (!h || !system) return Fail(APHCG_ERR_ARG, "null argument");
+  if (int rc = SetDevice(h)) return rc;
+  aphcg_layout l;
+  if (int rc = CheckLayout(h, layout, &l)) return rc;
+  if (int rc = EnsureStage(h)) return rc;
+  const Geom& g = h->g;
+  const size_t plane = (size_t)g.cz * 64;
+  const int per_chunk = (int)std::max<size_t>(1, kStageBytes / plane);
+  if (plane > kStageBytes) return Fail(APHCG_ERR_ARG, "xy-plane larger than the staging buffer");
+  int b = 0;
+  for (int k0 = 0; k0 < g.nzl; k0 += per_chunk, b ^= 1) {
+    const int nk = std::min(per_chunk, g.nzl - k0);
+    // copy engine fills stage[b] once the transpose that last read it is done
+    CK(cudaStreamWaitEvent(h->copy_stream, h->stage_free[b], 0));
+    if (int rc = CopyPlanes(h, h->stage[b], system, l, true, k0, nk, 64, cudaMemcpyHostToDevice,
+                            h->copy_stream))
+      return rc;
+    CK(cudaEventRecord(h->stage_ready[b], h->copy_stream));
+    CK(cudaStreamWaitEvent(h->stream, h->stage_ready[b], 0));
+    launch_rows_to_soa(g, h->stage[b], 0, g.cy, g.cz, k0, nk, h->coef, h->rhs, h->stream);
+    h->launches++;
+    CK(cudaEventRecord(h->stage_free[b], h->stream));
+  }
+  CK(cudaGetLastError());
+  h->have_system = true;
+  return 0;
+}
+
+int aphcg_set_system_device(aphcg_t* h, const double* d_system, const aphcg_layout* layout) {
+  if (!h || !d_system) return Fail(APHCG_ERR_ARG, "null argument");
+  if (int rc = SetDevice(h)) return rc;
+  aphcg_layout l;
+  if (int rc = CheckLayout(h, layout, &l)) return rc;
+  launch_rows_to_soa(h->g, d_system, l.offset, l.stride_y, l.stride_z, 0, h->g.nzl, h->coef,
+                     h->rhs, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  h->have_system = true;
+  return 0;
+}
+
+static int ScatterGuess(aphcg_t* h, const double* d_src, const aphcg_layout& l) {
+  launch_scatter_field(h->g, d_src, l.offset, l.stride_y, l.stride_z, h->u, h->d.p[1],
+                       h->d.p_lo_dst[1], h->d.p_hi_dst[1], h->vx, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  h->have_guess = true;
+  return 0;
+}
+
+int aphcg_upload_guess(aphcg_t* h, const double* x0, const aphcg_layout* layout) {
+  if (!h) return Fail(APHCG_ERR_ARG, "null handle");
+  if (int rc = SetDevice(h)) return rc;
+  aphcg_layout l;
+  if (int rc = CheckLayout(h, layout, &l)) return rc;
+  if (!x0) {
+    aphcg_layout c{0, h->g.cy, h->g.cz};
+    return ScatterGuess(h, nullptr, c);
+  }
+  // stage through Ap (free between solves): compact copy, then scatter
+  if (int rc = CopyPlanes(h, h->ap, x0, l, true, 0, h->g.nzl, 8, cudaMemcpyHostToDevice, h->stream))
+    return rc;
+  aphcg_layout c{0, h->g.cy, h->g.cz};
+  return ScatterGuess(h, h->ap, c);
+}
+
+int aphcg_set_guess_device(aphcg_t* h, const double* d_x0, const aphcg_layout* layout) {
+  if (!h) return Fail(APHCG_ERR_ARG, "null handle");
+  if (int rc = SetDevice(h)) return rc;
+  aphcg_layout l;
+  if (int rc = CheckLayout(h, layout, &l)) return rc;
+  return ScatterGuess(h, d_x0, l);
+}
+
+// ---- run -----------------------------------------------------------------------
+static int CheckRun(aphcg_t* h, const aphcg_conf* conf) {
+  if (!h || !conf) return Fail(APHCG_ERR_ARG, "null argument");
+  if (!h->have_system) return Fail(APHCG_ERR_STATE, "no system uploaded");
+  if (conf->maxiter < 0 || conf->miniter < 0) return Fail(APHCG_ERR_ARG, "negative iteration limit");
+  if (!h->single && (!h->comm || !h->connected))
+    return Fail(APHCG_ERR_STATE, "nranks > 1 needs aphcg_comm_init and aphcg_ipc_connect first");
+  return 0;
+}
+
+static int FinishRun(aphcg_t* h, aphcg_info* info) {
+  CK(cudaEventRecord(h->ev[2], h->stream));
+  CK(cudaMemcpyAsync(h->h_st, h->st, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  h->last_iter = h->h_st->iter;
+  h->have_guess = false;  // the guess buffers were consumed
+  if (info) {
+    info->residual = h->h_st->residual;
+    info->iter = h->h_st->iter;
+    info->reserved = 0;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]));
+    info->loop_ms = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]));
+    info->total_ms = ms;
+  }
+  return 0;
+}
+
+int aphcg_run(aphcg_t* h, const aphcg_conf* conf, aphcg_info* info) {
+  if (int rc = CheckRun(h, conf)) return rc;
+  if (int rc = SetDevice(h)) return rc;
+  if (!h->have_guess) {
+    if (int rc = aphcg_upload_guess(h, nullptr, nullptr)) return rc;
+  }
+  if (int rc = EnsureHistory(h, conf->maxiter)) return rc;
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  if (int rc = WriteState(h, conf)) return rc;
+  // p_{-1} = 0: the first direction is p = r + 0*0 (linear.ipp:59-62)
+  CK(cudaMemsetAsync(h->d.p[0], 0, sizeof(double) * (size_t)h->g.ptotal, h->stream));
+  if (int rc = StreamBarrier(h)) return rc;  // neighbours' guess planes have landed
+  launch_init_residual(h->g, h->d, h->vx, h->single, h->stream);
+  h->launches++;
+  if (!h->single) {
+    if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
+    launch_finish_init(h->d, h->stream);
+    h->launches++;
+  }
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  if (int rc = RunLoop(h, false, conf)) return rc;
+  launch_final_update(h->g, h->d, h->vx, h->stream);
+  h->launches++;
+  return FinishRun(h, info);
+}
+
+int aphcg_run_jacobi(aphcg_t* h, const aphcg_conf* conf, aphcg_info* info) {
+  if (int rc = CheckRun(h, conf)) return rc;
+  if (int rc = SetDevice(h)) return rc;
+  if (!h->have_guess) {
+    if (int rc = aphcg_upload_guess(h, nullptr, nullptr)) return rc;
+  }
+  if (int rc = EnsureHistory(h, conf->maxiter)) return rc;
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  if (int rc = WriteState(h, conf)) return rc;
+  if (int rc = StreamBarrier(h)) return rc;  // neighbours' guess planes have landed
+  // iterate starts in p[0] (parity of iter = 0): copy the padded guess over
+  CK(cudaMemcpyAsync(h->d.p[0], h->d.p[1], sizeof(double) * (size_t)h->g.ptotal,
+                     cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  if (int rc = RunLoop(h, true, conf)) return rc;
+  // result: inner cells of the current iterate -> compact u
+  {
+    const Geom& g = h->g;
+    const double* cur = h->d.p[h->h_st->iter & 1];
+    CK(cudaMemcpy2DAsync(h->u, sizeof(double) * g.nx, cur + g.poff, sizeof(double) * g.py,
+                         sizeof(double) * g.nx, (size_t)g.ny, cudaMemcpyDeviceToDevice, h->stream));
+    // planes are not contiguous in the padded layout (ghost rows in between)
+    for (int k = 1; k < g.nzl; ++k)
+      CK(cudaMemcpy2DAsync(h->u + k * g.cz, sizeof(double) * g.nx, cur + g.poff + k * g.pz,
+                           sizeof(double) * g.py, sizeof(double) * g.nx, (size_t)g.ny,
+                           cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return FinishRun(h, info);
+}
+
+int aphcg_download_solution(aphcg_t* h, double* x, const aphcg_layout* layout) {
+  if (!h || !x) return Fail(APHCG_ERR_ARG, "null argument");
+  if (int rc = SetDevice(h)) return rc;
+  aphcg_layout l;
+  if (int rc = CheckLayout(h, layout, &l)) return rc;
+  if (int rc = CopyPlanes(h, x, h->u, l, false, 0, h->g.nzl, 8, cudaMemcpyDeviceToHost, h->stream))
+    return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int aphcg_get_solution_device(aphcg_t* h, double* d_x, const aphcg_layout* layout) {
+  if (!h || !d_x) return Fail(APHCG_ERR_ARG, "null argument");
+  if (int rc = SetDevice(h)) return rc;
+  aphcg_layout l;
+  if (int rc = CheckLayout(h, layout, &l)) return rc;
+  launch_gather_field(h->g, h->u, d_x, l.offset, l.stride_y, l.stride_z, h->stream);
+  h->launches++;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int aphcg_get_history(aphcg_t* h, double* out, int32_t n) {
+  if (!h || !out || n < 0) return Fail(APHCG_ERR_ARG, "bad argument");
+  if (int rc = SetDevice(h)) return rc;
+  n = std::min<int32_t>(n, std::min(h->last_iter, h->hist_cap));
+  if (n > 0) CK(cudaMemcpy(out, h->history, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return n;
+}
+
+int aphcg_solve(aphcg_t* h, const double* system, const aphcg_layout* system_layout,
+                const double* x0, const aphcg_layout* x0_layout, double* x,
+                const aphcg_layout* x_layout, const aphcg_conf* conf, aphcg_info* info) {
+  if (!h || !system || !x || !conf) return Fail(APHCG_ERR_ARG, "null argument");
+  if (int rc = aphcg_upload_system(h, system, system_layout)) return rc;
+  if (int rc = aphcg_upload_guess(h, x0, x0_layout)) return rc;
+  if (int rc = aphcg_run(h, conf, info)) return rc;
+  return aphcg_download_solution(h, x, x_layout);
+}
+
+int aphcg_apply(aphcg_t* h, const double* v, const aphcg_layout* v_layout, double* out,
+                const aphcg_layout* out_layout) {
+  if (!h || !v || !out) return Fail(APHCG_ERR_ARG, "null argument");
+  if (!h->have_system) return Fail(APHCG_ERR_STATE, "no system uploaded");
+  if (int rc = SetDevice(h)) return rc;
+  aphcg_layout lv, lo;
+  if (int rc = CheckLayout(h, v_layout, &lv)) return rc;
+  if (int rc = CheckLayout(h, out_layout, &lo)) return rc;
+  if (int rc = CopyPlanes(h, h->ap, v, lv, true, 0, h->g.nzl, 8, cudaMemcpyHostToDevice, h->stream))
+    return rc;
+  launch_scatter_field(h->g, h->ap, 0, h->g.cy, h->g.cz, nullptr, h->d.p[1], h->d.p_lo_dst[1],
+                       h->d.p_hi_dst[1], h->vx, h->stream);
+  if (int rc = StreamBarrier(h)) return rc;
+  launch_apply(h->g, h->d, h->vx, h->stream);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  if (int rc = CopyPlanes(h, out, h->ap, lo, false, 0, h->g.nzl, 8, cudaMemcpyDeviceToHost,
+                          h->stream))
+    return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_guess = false;
+  return 0;
+}
+
+int aphcg_assemble_spheres(aphcg_t* h, const double* spheres, int32_t nspheres, double rho_in,
+                           double rho_out, double dt) {
+  if (!h || (nspheres > 0 && !spheres) || nspheres < 0) return Fail(APHCG_ERR_ARG, "bad argument");
+  if (int rc = SetDevice(h)) return rc;
+  double* d_sph = nullptr;
+  if (nspheres > 0) {
+    CK(cudaMalloc(&d_sph, sizeof(double) * 4 * (size_t)nspheres));
+    CK(cudaMemcpyAsync(d_sph, spheres, sizeof(double) * 4 * (size_t)nspheres,
+                       cudaMemcpyHostToDevice, h->stream));
+  }
+  int per[3] = {h->desc.periodic[0], h->desc.periodic[1], h->desc.periodic[2]};
+  launch_assemble_spheres(h->g, h->d, h->coef, h->rhs, d_sph, nspheres, rho_in, rho_out, dt,
+                          h->desc.nz, h->desc.z0, (int)h->desc.nx, (int)h->desc.ny, per, h->stream);
+  h->launches += 2;
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (d_sph) cudaFree(d_sph);
+  if (e != cudaSuccess) return Fail(APHCG_ERR_CUDA, "assemble failed: %s", cudaGetErrorString(e));
+  CK(cudaGetLastError());
+  h->have_system = true;
+  h->have_guess = false;
+  return 0;
+}
+
+int aphcg_download_system(aphcg_t* h, double* system, const aphcg_layout* layout) {
+  if (!h || !system) return Fail(APHCG_ERR_ARG, "null argument");
+  if (!h->have_system) return Fail(APHCG_ERR_STATE, "no system resident");
+  if (int rc = SetDevice(h)) return rc;
+  aphcg_layout l;
+  if (int rc = CheckLayout(h, layout, &l)) return rc;
+  double* d_rows = nullptr;
+  CK(cudaMalloc(&d_rows, (size_t)h->g.ncell * 64));
+  launch_soa_to_rows(h->g, h->d, d_rows, h->stream);
+  h->launches++;
+  int rc = CopyPlanes(h, system, d_rows, l, false, 0, h->g.nzl, 64, cudaMemcpyDeviceToHost,
+                      h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_rows);
+  if (rc) return rc;
+  if (e != cudaSuccess) return Fail(APHCG_ERR_CUDA, "download failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------
+int aphcg_comm_unique_id(void* id_out) {
+  if (!id_out) return Fail(APHCG_ERR_ARG, "null argument");
+  if (const char* e = Nccl().Load()) return Fail(APHCG_ERR_COMM, "%s", e);
+  ncclUniqueId id;
+  NK(Nccl().GetUniqueId(&id));
+  memset(id_out, 0, APHCG_UNIQUE_ID_BYTES);
+  memcpy(id_out, &id, sizeof(id));
+  return 0;
+}
+
+int aphcg_comm_init(aphcg_t* h, const void* id) {
+  if (!h || !id) return Fail(APHCG_ERR_ARG, "null argument");
+  if (h->single) return 0;
+  if (const char* e = Nccl().Load()) return Fail(APHCG_ERR_COMM, "%s", e);
+  if (int rc = SetDevice(h)) return rc;
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  NK(Nccl().CommInitRank(&h->comm, h->desc.nranks, uid, h->desc.rank));
+  return 0;
+}
+
+int aphcg_ipc_export(aphcg_t* h, void* blob_out) {
+  if (!h || !blob_out) return Fail(APHCG_ERR_ARG, "null argument");
+  if (int rc = SetDevice(h)) return rc;
+  IpcBlob b{};
+  CK(cudaIpcGetMemHandle(&b.handle, h->slab));
+  b.ptotal = h->g.ptotal;
+  b.pz = h->g.pz;
+  b.poff = h->g.poff;
+  b.nzl = h->g.nzl;
+  b.rank = h->desc.rank;
+  b.pid = (int32_t)getpid();
+  b.base = (uint64_t)(uintptr_t)h->slab;
+  memset(blob_out, 0, APHCG_IPC_BYTES);
+  memcpy(blob_out, &b, sizeof(b));
+  return 0;
+}
+
+int aphcg_ipc_connect(aphcg_t* h, const void* lo_blob, const void* hi_blob) {
+  if (!h) return Fail(APHCG_ERR_ARG, "null handle");
+  if (h->single) return 0;
+  if (int rc = SetDevice(h)) return rc;
+  const Geom& g = h->g;
+  IpcBlob lo{}, hi{};
+  if (lo_blob) memcpy(&lo, lo_blob, sizeof(lo));
+  if (hi_blob) memcpy(&hi, hi_blob, sizeof(hi));
+  auto open = [&](const IpcBlob& b, void** out, bool* opened) -> int {
+    if (b.pz != g.pz || b.poff != g.poff)
+      return Fail(APHCG_ERR_COMM, "neighbour slab has a different xy layout");
+    if (b.pid == (int32_t)getpid()) {  // same process: plain peer pointer
+      *out = (void*)(uintptr_t)b.base;
+      *opened = false;
+      return 0;
+    }
+    CK(cudaIpcOpenMemHandle(out, b.handle, cudaIpcMemLazyEnablePeerAccess));
+    *opened = true;
+    return 0;
+  };
+  if (lo_blob) {
+    if (int rc = open(lo, &h->peer_lo, &h->peer_lo_opened)) return rc;
+  }
+  if (hi_blob) {
+    if (lo_blob && lo.rank == hi.rank) {  // two ranks, periodic: same neighbour both ways
+      h->peer_hi = h->peer_lo;
+      h->peer_hi_opened = false;
+    } else if (int rc = open(hi, &h->peer_hi, &h->peer_hi_opened)) {
+      return rc;
+    }
+  }
+  DevPtrs& d = h->d;
+  if (lo_blob) {  // my bottom plane -> lower neighbour's top ghost plane
+    double* base = (double*)h->peer_lo;
+    const int64_t off = lo.poff + lo.nzl * lo.pz;
+    d.r_lo_dst = base + off;
+    d.p_lo_dst[0] = base + lo.ptotal + off;
+    d.p_lo_dst[1] = base + 2 * lo.ptotal + off;
+  }
+  if (hi_blob) {  // my top plane -> upper neighbour's bottom ghost plane
+    double* base = (double*)h->peer_hi;
+    const int64_t off = hi.poff - hi.pz;
+    d.r_hi_dst = base + off;
+    d.p_hi_dst[0] = base + hi.ptotal + off;
+    d.p_hi_dst[1] = base + 2 * hi.ptotal + off;
+  }
+  h->connected = true;
+  InvalidateGraphs(h);
+  return 0;
+}
+
+int aphcg_timer_start(aphcg_t* h) {
+  if (!h) return Fail(APHCG_ERR_ARG, "null handle");
+  if (int rc = SetDevice(h)) return rc;
+  CK(cudaEventRecord(h->ev[3], h->stream));
+  return 0;
+}
+
+int aphcg_timer_stop(aphcg_t* h, double* ms) {
+  if (!h || !ms) return Fail(APHCG_ERR_ARG, "null argument");
+  if (int rc = SetDevice(h)) return rc;
+  cudaEvent_t e;
+  CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(e, h->stream));
+  CK(cudaEventSynchronize(e));
+  float f = 0;
+  cudaError_t err = cudaEventElapsedTime(&f, h->ev[3], e);
+  cudaEventDestroy(e);
+  if (err != cudaSuccess) return Fail(APHCG_ERR_CUDA, "timer: %s", cudaGetErrorString(err));
+  *ms = f;
+  return 0;
+}
+
+int aphcg_profile_kernels(aphcg_t* h, int32_t iters, double* ms_dir_spmv, double* ms_update) {
+  if (!h || iters < 1 || !ms_dir_spmv || !ms_update) return Fail(APHCG_ERR_ARG, "bad argument");
+  aphcg_conf conf{0.0, 0, iters + 1};
+  if (int rc = CheckRun(h, &conf)) return rc;
+  if (!h->single) return Fail(APHCG_ERR_STATE, "kernel profiling is single-rank only");
+  if (int rc = SetDevice(h)) return rc;
+  if (!h->have_guess) {
+    if (int rc = aphcg_upload_guess(h, nullptr, nullptr)) return rc;
+  }
+  if (int rc = EnsureHistory(h, conf.maxiter)) return rc;
+  if (int rc = WriteState(h, &conf)) return rc;
+  CK(cudaMemsetAsync(h->d.p[0], 0, sizeof(double) * (size_t)h->g.ptotal, h->stream));
+  launch_init_residual(h->g, h->d, h->vx, true, h->stream);
+  std::vector<cudaEvent_t> ev(3 * (size_t)iters);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  for (int i = 0; i < iters; ++i) {
+    CK(cudaEventRecord(ev[3 * i], h->stream));
+    if (h->use_tma) {
+      launch_dir_spmv_tma(h->tma, h->g, h->d, true, h->stream);
+    } else {
+      launch_dir_spmv_plain(h->g, h->d, h->vx, true, h->stream);
+    }
+    CK(cudaEventRecord(ev[3 * i + 1], h->stream));
+    launch_update(h->g, h->d, h->vx, true, h->stream);
+    CK(cudaEventRecord(ev[3 * i + 2], h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  double sd = 0, su = 0;
+  for (int i = 0; i < iters; ++i) {
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, ev[3 * i], ev[3 * i + 1]));
+    CK(cudaEventElapsedTime(&b, ev[3 * i + 1], ev[3 * i + 2]));
+    sd += a;
+    su += b;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  *ms_dir_spmv = sd / iters;
+  *ms_update = su / iters;
+  h->launches += 1 + 2 * (int64_t)iters;
+  h->have_guess = false;
+  return 0;
+}
+
+void* aphcg_stream(aphcg_t* h) { return h ? (void*)h->stream : nullptr; }
+int64_t aphcg_launch_count(aphcg_t* h) { return h ? h->launches : 0; }
+int aphcg_launches_per_iter(aphcg_t* h) { return h ? LaunchesPerIter(h) : 0; }
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+// Device-side assembly of the synthetic variable-density projection systems
+// S2..S4 of SURVEY.md 8(d) (used by benchmarks whose rows would not fit in host
+// memory, and as a first step towards assembling the pressure system where it is
+// solved).  Restates the reference's face formulas (src/solver/proj.ipp:343-398):
+//   a_f = h*dt/rho_f,  rho_f = 2/(1/rho_- + 1/rho_+),  zero through non-periodic
+//   domain faces;  e0 = sum_f a_f,  e[1+q] = -a_f(q),
+//   e7 = sum_q outward(q)*v_f,  v_f = (u.n_f)*h^2,
+//   u = (sin 2pi x cos 2pi y, -cos 2pi x sin 2pi y, 0).
+// Arithmetic is written with explicit round-to-nearest intrinsics so that the
+// sphere classification matches aphros_b200/systems.py bit for bit.
+#include "cg_kernels.cuh"
+#include "cg_launch.h"
+
+namespace acg {
+
+namespace {
+
+struct AsmPar {
+  int nx_g, ny_g;
+  int64_t nz_g, z0;
+  int per[3];
+  double h, rho_in, rho_out, dt;
+  int nspheres;
+};
+
+// density at global cell (i,j,k), periodic wrap where the domain is periodic
+__device__ double rho_at(const AsmPar& P, const double* __restrict__ sph, int i, int j,
+                         int64_t k) {
+  if (P.per[0]) i = (i + P.nx_g) % P.nx_g;
+  if (P.per[1]) j = (j + P.ny_g) % P.ny_g;
+  if (P.per[2]) k = (k + P.nz_g) % P.nz_g;
+  const double x = __dmul_rn((double)i + 0.5, P.h);
+  const double y = __dmul_rn((double)j + 0.5, P.h);
+  const double z = __dmul_rn((double)k + 0.5, P.h);
+  bool inside = false;
+  for (int s = 0; s < P.nspheres; ++s) {
+    const double dx = __dsub_rn(x, sph[4 * s + 0]);
+    const double dy = __dsub_rn(y, sph[4 * s + 1]);
+    const double dz = __dsub_rn(z, sph[4 * s + 2]);
+    const double r = sph[4 * s + 3];
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    inside = inside || (d2 < __dmul_rn(r, r));
+  }
+  return inside ? P.rho_in : P.rho_out;
+}
+
+// pass 1: density into a padded field (ghost layers included)
+__global__ void k_density(const Geom g, const AsmPar P, const double* __restrict__ sph,
+                          double* rho) {
+  const int64_t nxy = (int64_t)(g.nx + 2) * (g.ny + 2);
+  const int64_t n = nxy * (g.nzl + 2);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t % (g.nx + 2)) - 1;
+    const int j = (int)((t / (g.nx + 2)) % (g.ny + 2)) - 1;
+    const int k = (int)(t / nxy) - 1;
+    rho[g.poff + i + (int64_t)j * g.py + (int64_t)k * g.pz] = rho_at(P, sph, i, j, P.z0 + k);
+  }
+}
+
+// pass 2: rows from the padded density
+__global__ void k_rows_from_density(const Geom g, const AsmPar P, const double* __restrict__ rho,
+                                    double* a0, double* a1, double* a2, double* a3, double* a4,
+                                    double* a5, double* a6, double* rhs) {
+  const double two_pi = 6.283185307179586476925286766559;
+  const double hh = __dmul_rn(P.h, P.h);
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < g.ncell;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(c % g.nx);
+    const int j = (int)((c / g.nx) % g.ny);
+    const int k = (int)(c / g.cz);
+    const int64_t kg = P.z0 + k;
+    const int64_t ip = g.poff + i + (int64_t)j * g.py + (int64_t)k * g.pz;
+    const double rc = rho[ip];
+    const int64_t off[6] = {-1, 1, -g.py, g.py, -g.pz, g.pz};
+    const bool wall[6] = {!P.per[0] && i == 0,          !P.per[0] && i == P.nx_g - 1,
+                          !P.per[1] && j == 0,          !P.per[1] && j == P.ny_g - 1,
+                          !P.per[2] && kg == 0,         !P.per[2] && kg == P.nz_g - 1};
+    double a[6];
+    double diag = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const double rn = rho[ip + off[q]];
+      // harmonic mean with the lower cell first, as systems.py forms it
+      const double rlo = (q & 1) ? rc : rn, rhi = (q & 1) ? rn : rc;
+      const double rf = __ddiv_rn(2.0, __dadd_rn(__ddiv_rn(1.0, rlo), __ddiv_rn(1.0, rhi)));
+      a[q] = wall[q] ? 0.0 : __ddiv_rn(__dmul_rn(P.h, P.dt), rf);
+      diag = __dadd_rn(diag, a[q]);
+    }
+    a0[c] = diag;
+    a1[c] = -a[0];
+    a2[c] = -a[1];
+    a3[c] = -a[2];
+    a4[c] = -a[3];
+    a5[c] = -a[4];
+    a6[c] = -a[5];
+    // e7: divergence of the face-normal velocity (zero normal velocity on the walls)
+    const double xc = __dmul_rn((double)i + 0.5, P.h), yc = __dmul_rn((double)j + 0.5, P.h);
+    const double xf0 = __dmul_rn((double)i, P.h), xf1 = __dmul_rn((double)(i + 1), P.h);
+    const double yf0 = __dmul_rn((double)j, P.h), yf1 = __dmul_rn((double)(j + 1), P.h);
+    const double cy = cos(two_pi * yc), cx = cos(two_pi * xc);
+    double vx0 = sin(two_pi * xf0) * cy * hh, vx1 = sin(two_pi * xf1) * cy * hh;
+    double vy0 = -cx * sin(two_pi * yf0) * hh, vy1 = -cx * sin(two_pi * yf1) * hh;
+    if (i == 0) vx0 = 0.0;
+    if (i == P.nx_g - 1) vx1 = 0.0;
+    if (j == 0) vy0 = 0.0;
+    if (j == P.ny_g - 1) vy1 = 0.0;
+    rhs[c] = __dadd_rn(__dsub_rn(vx1, vx0), __dsub_rn(vy1, vy0));
+  }
+}
+
+}  // namespace
+
+void launch_assemble_spheres(const Geom& g, const DevPtrs& d, double* const* a, double* rhs,
+                             const double* spheres, int nspheres, double rho_in, double rho_out,
+                             double dt, int64_t nz_global, int64_t z0, int nx_g, int ny_g,
+                             const int* periodic, cudaStream_t s) {
+  AsmPar P;
+  P.nx_g = nx_g;
+  P.ny_g = ny_g;
+  P.nz_g = nz_global;
+  P.z0 = z0;
+  for (int i = 0; i < 3; ++i) P.per[i] = periodic[i];
+  const int64_t nmax = std::max<int64_t>(std::max<int64_t>(nx_g, ny_g), nz_global);
+  P.h = 1.0 / (double)nmax;
+  P.rho_in = rho_in;
+  P.rho_out = rho_out;
+  P.dt = dt;
+  P.nspheres = nspheres;
+  // density goes through p[1] (free between solves); its ghost layers are
+  // restored to zero afterwards because the solver relies on zero ghosts at
+  // non-periodic boundaries.
+  k_density<<<148 * 8, 256, 0, s>>>(g, P, spheres, d.p[1]);
+  k_rows_from_density<<<148 * 8, 256, 0, s>>>(g, P, d.p[1], a[0], a[1], a[2], a[3], a[4], a[5],
+                                              a[6], rhs);
+  cudaMemsetAsync(d.p[1], 0, sizeof(double) * (size_t)g.ptotal, s);
+}
+
+}  // namespace acg

@@ -1,0 +1,562 @@
+// Hand-written FP64 CUDA kernels (sm_100a) of the CG hot path.
+//
+// Reference algorithm: linear::SolverConjugate<M>::Imp::Solve
+// (src/linear/linear.ipp:42-125).  One iteration there is four stages and
+// three sweeps over memory; here it is two kernels:
+//
+//   k_dir_spmv  ("iter3" of the previous iteration + "iter"):
+//       x  += alpha_prev * p_old          (the x update of "iter2", deferred)
+//       p   = r + beta * p_old            (on the tile and its 6 face neighbours)
+//       Ap  = A p ,  partial sum p.Ap
+//   k_update    ("iter2" + "check"):
+//       r  -= alpha * Ap ,  partial sums r.r and max|r| ,  ghost copies of r
+//
+// The halo exchange of the reference (m.Comm(&p, direct_one), linear.ipp:100)
+// disappears: ghost layers of p are recomputed locally from the ghost layers of
+// r and p_old (bitwise the same numbers the owner computes), and ghost layers of
+// r are written by k_update itself -- into this GPU's own ghost cells for
+// periodic wrap, or straight into the neighbour GPU's ghost plane over NVLink.
+#include "cg_kernels.cuh"
+#include "cg_launch.h"
+
+namespace acg {
+
+namespace {
+
+constexpr int kBX = 32;  // threads along x (one warp = one contiguous row segment)
+constexpr int kBY = 8;   // rows per block
+constexpr int kZC = 8;   // planes marched by one block
+
+struct Tile {
+  int i, j, k0, k1;
+  bool active;
+};
+
+template <int VX>
+__device__ __forceinline__ Tile my_tile(const Geom& g) {
+  Tile t;
+  t.i = (blockIdx.x * kBX + threadIdx.x) * VX;
+  t.j = blockIdx.y * kBY + threadIdx.y;
+  t.k0 = blockIdx.z * kZC;
+  t.k1 = min(t.k0 + kZC, g.nzl);
+  t.active = (t.i < g.nx) && (t.j < g.ny);
+  return t;
+}
+
+__device__ __forceinline__ unsigned num_blocks() { return gridDim.x * gridDim.y * gridDim.z; }
+__device__ __forceinline__ unsigned block_id() {
+  return blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+}
+
+// Stores the ghost copies of freshly computed inner values of a padded field:
+// periodic images in x and y inside the slab, and the z images through
+// lo_dst / hi_dst (own ghost plane or the neighbour GPU's, nullptr if none).
+template <int VX>
+__device__ __forceinline__ void store_images(const Geom& g, double* f, int64_t idp, int i, int j,
+                                             int k, const Vec<VX>& val, double* lo_dst,
+                                             double* hi_dst) {
+  if (g.per_x) {
+    if (i == 0) f[idp + g.nx] = val.v[0];
+    if (i + VX == g.nx) f[idp - i - 1] = val.v[VX - 1];
+  }
+  if (g.per_y) {
+    if (j == 0) stv<VX>(f + idp + (int64_t)g.ny * g.py, val);
+    if (j == g.ny - 1) stv<VX>(f + idp - (int64_t)g.ny * g.py, val);
+  }
+  if (k == 0 && lo_dst) stv<VX>(lo_dst + i + (int64_t)j * g.py, val);
+  if (k == g.nzl - 1 && hi_dst) stv<VX>(hi_dst + i + (int64_t)j * g.py, val);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------
+// k_dir_spmv (plain-load variant): neighbours of p come through L1/L2.
+// ------------------------------------------------------------------------------
+template <int VX, bool kSingle>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_dir_spmv_plain(const Geom g, const DevPtrs d) {
+  __shared__ double sm[32];
+  __shared__ int sm_flag;
+  CgState* st = d.st;
+  if (st->done) return;
+  const double beta = cg_beta(st);
+  const double alpha_prev = st->alpha_prev;
+  const int par = st->iter & 1;
+  const double* __restrict__ po = d.p[par];
+  double* __restrict__ pn = d.p[par ^ 1];
+  const double* __restrict__ r = d.r;
+
+  const Tile t = my_tile<VX>(g);
+  double acc = 0.0;
+  if (t.active) {
+    for (int k = t.k0; k < t.k1; ++k) {
+      const int64_t idc = t.i + t.j * g.cy + k * g.cz;
+      const int64_t idp = g.poff + t.i + t.j * g.py + k * g.pz;
+      // p_new = r + beta*p_old (linear.ipp:97-99) at the cells and their neighbours
+      auto pnew = [&](int64_t off) {
+        const Vec<VX> rr = ldv<VX>(r + off), pp = ldv<VX>(po + off);
+        Vec<VX> o;
+#pragma unroll
+        for (int v = 0; v < VX; ++v) o.v[v] = fma(beta, pp.v[v], rr.v[v]);
+        return o;
+      };
+      auto pnew1 = [&](int64_t off) { return fma(beta, po[off], r[off]); };
+      const Vec<VX> pold_c = ldv<VX>(po + idp);
+      const Vec<VX> r_c = ldv<VX>(r + idp);
+      Vec<VX> pc;
+#pragma unroll
+      for (int v = 0; v < VX; ++v) pc.v[v] = fma(beta, pold_c.v[v], r_c.v[v]);
+      const double pxm = pnew1(idp - 1);
+      const double pxp = pnew1(idp + VX);
+      const Vec<VX> pym = pnew(idp - g.py), pyp = pnew(idp + g.py);
+      const Vec<VX> pzm = pnew(idp - g.pz), pzp = pnew(idp + g.pz);
+
+      Vec<VX> a[7];
+#pragma unroll
+      for (int q = 0; q < 7; ++q) a[q] = ldv_stream<VX>(d.a[q] + idc);
+      Vec<VX> uu = ldv_stream<VX>(d.u + idc);
+      Vec<VX> ap;
+#pragma unroll
+      for (int v = 0; v < VX; ++v) {
+        const double xm = (v == 0) ? pxm : pc.v[v - 1];
+        const double xp = (v == VX - 1) ? pxp : pc.v[v + 1];
+        // accumulation order of the reference: centre, then q = 0..5 (linear.ipp:67-70)
+        double s = pc.v[v] * a[0].v[v];
+        s = fma(xm, a[1].v[v], s);
+        s = fma(xp, a[2].v[v], s);
+        s = fma(pym.v[v], a[3].v[v], s);
+        s = fma(pyp.v[v], a[4].v[v], s);
+        s = fma(pzm.v[v], a[5].v[v], s);
+        s = fma(pzp.v[v], a[6].v[v], s);
+        ap.v[v] = s;
+        acc = fma(pc.v[v], s, acc);
+        uu.v[v] = fma(alpha_prev, pold_c.v[v], uu.v[v]);  // linear.ipp:88, one iteration late
+      }
+      stv_stream<VX>(d.ap + idc, ap);
+      stv_stream<VX>(d.u + idc, uu);
+      stv<VX>(pn + idp, pc);
+      // ghost cells of p_new owned by this thread
+      if (t.i == 0) pn[idp - 1] = pxm;
+      if (t.i + VX == g.nx) pn[idp + VX] = pxp;
+      if (t.j == 0) stv<VX>(pn + idp - g.py, pym);
+      if (t.j == g.ny - 1) stv<VX>(pn + idp + g.py, pyp);
+      if (k == 0) stv<VX>(pn + idp - g.pz, pzm);
+      if (k == g.nzl - 1) stv<VX>(pn + idp + g.pz, pzp);
+    }
+  }
+  const double bsum = block_reduce<false>(acc, sm);
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  if (tid == 0) d.partials[block_id()] = bsum;
+  if (last_block(&st->counter_a, num_blocks(), &sm_flag)) {
+    const double tot = reduce_slots<false>(d.partials, num_blocks(), sm);
+    if (tid == 0) {
+      st->loc_sum = tot;
+      if (kSingle) cg_finish_dir(st, tot);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------
+// k_update: r -= alpha*Ap, sum r^2, max|r|, ghost copies of r ("iter2"+"check").
+// ------------------------------------------------------------------------------
+template <int VX, bool kSingle>
+__global__ void __launch_bounds__(kBX* kBY) k_update(const Geom g, const DevPtrs d) {
+  __shared__ double sm[32];
+  __shared__ int sm_flag;
+  CgState* st = d.st;
+  if (st->done) return;
+  const double alpha = cg_alpha(st);
+  double* __restrict__ r = d.r;
+  const Tile t = my_tile<VX>(g);
+  double acc = 0.0, amax = 0.0;
+  if (t.active) {
+    for (int k = t.k0; k < t.k1; ++k) {
+      const int64_t idc = t.i + t.j * g.cy + k * g.cz;
+      const int64_t idp = g.poff + t.i + t.j * g.py + k * g.pz;
+      const Vec<VX> ap = ldv_stream<VX>(d.ap + idc);
+      Vec<VX> rv = ldv<VX>(r + idp);
+#pragma unroll
+      for (int v = 0; v < VX; ++v) {
+        rv.v[v] = fma(-alpha, ap.v[v], rv.v[v]);  // linear.ipp:89
+        acc = fma(rv.v[v], rv.v[v], acc);         // :90
+        amax = fmax(amax, fabs(rv.v[v]));         // :91
+      }
+      stv<VX>(r + idp, rv);
+      store_images<VX>(g, r, idp, t.i, t.j, k, rv, d.r_lo_dst, d.r_hi_dst);
+    }
+  }
+  if (d.r_lo_dst != nullptr || d.r_hi_dst != nullptr) __threadfence_system();
+  const double bsum = block_reduce<false>(acc, sm);
+  const double bmax = block_reduce<true>(amax, sm);
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  if (tid == 0) {
+    d.partials[block_id()] = bsum;
+    d.partials2[block_id()] = bmax;
+  }
+  if (last_block(&st->counter_b, num_blocks(), &sm_flag)) {
+    const double tot = reduce_slots<false>(d.partials, num_blocks(), sm);
+    const double mx = reduce_slots<true>(d.partials2, num_blocks(), sm);
+    if (tid == 0) {
+      st->loc_sum = tot;
+      st->loc_max = mx;
+      if (kSingle) cg_finish_upd(st, d.history, tot, mx);
+    }
+  }
+}
+
+// Multi-GPU: runs after the all-reduce of loc_sum / loc_max.
+__global__ void k_finish_dir(CgState* st) {
+  if (st->done) return;
+  cg_finish_dir(st, st->loc_sum);
+}
+__global__ void k_finish_upd(CgState* st, double* history) {
+  if (st->done) return;
+  cg_finish_upd(st, history, st->loc_sum, st->loc_max);
+}
+__global__ void k_finish_init(CgState* st) { st->rr = st->loc_sum; }
+
+// ------------------------------------------------------------------------------
+// k_residual: out = sign*(A f [+ rhs]) from a padded field f (stage "init",
+// linear.ipp:48-56, with sign=-1 and rhs; the bare operator with sign=+1).
+// kToPadded: result goes to the padded residual (with ghost copies) and sum r^2
+// is formed; otherwise to a compact array.
+// ------------------------------------------------------------------------------
+template <int VX, bool kInit, bool kSingle>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_residual(const Geom g, const DevPtrs d, const double* __restrict__ f, double* out) {
+  __shared__ double sm[32];
+  __shared__ int sm_flag;
+  CgState* st = d.st;
+  const Tile t = my_tile<VX>(g);
+  double acc = 0.0;
+  if (t.active) {
+    for (int k = t.k0; k < t.k1; ++k) {
+      const int64_t idc = t.i + t.j * g.cy + k * g.cz;
+      const int64_t idp = g.poff + t.i + t.j * g.py + k * g.pz;
+      const Vec<VX> fc = ldv<VX>(f + idp);
+      const double fxm = f[idp - 1], fxp = f[idp + VX];
+      const Vec<VX> fym = ldv<VX>(f + idp - g.py), fyp = ldv<VX>(f + idp + g.py);
+      const Vec<VX> fzm = ldv<VX>(f + idp - g.pz), fzp = ldv<VX>(f + idp + g.pz);
+      Vec<VX> a[7];
+#pragma unroll
+      for (int q = 0; q < 7; ++q) a[q] = ldv_stream<VX>(d.a[q] + idc);
+      Vec<VX> b;
+      if (kInit) b = ldv_stream<VX>(d.rhs + idc);
+      Vec<VX> res;
+#pragma unroll
+      for (int v = 0; v < VX; ++v) {
+        const double xm = (v == 0) ? fxm : fc.v[v - 1];
+        const double xp = (v == VX - 1) ? fxp : fc.v[v + 1];
+        // linear.ipp:50-53: u*e0 + e7, then neighbours q = 0..5
+        double s = kInit ? fma(fc.v[v], a[0].v[v], b.v[v]) : fc.v[v] * a[0].v[v];
+        s = fma(xm, a[1].v[v], s);
+        s = fma(xp, a[2].v[v], s);
+        s = fma(fym.v[v], a[3].v[v], s);
+        s = fma(fyp.v[v], a[4].v[v], s);
+        s = fma(fzm.v[v], a[5].v[v], s);
+        s = fma(fzp.v[v], a[6].v[v], s);
+        res.v[v] = kInit ? -s : s;
+        acc = fma(res.v[v], res.v[v], acc);
+      }
+      if (kInit) {
+        stv<VX>(out + idp, res);
+        store_images<VX>(g, out, idp, t.i, t.j, k, res, d.r_lo_dst, d.r_hi_dst);
+      } else {
+        stv<VX>(out + idc, res);
+      }
+    }
+  }
+  if (!kInit) return;
+  if (d.r_lo_dst != nullptr || d.r_hi_dst != nullptr) __threadfence_system();
+  const double bsum = block_reduce<false>(acc, sm);
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  if (tid == 0) d.partials[block_id()] = bsum;
+  if (last_block(&st->counter_a, num_blocks(), &sm_flag)) {
+    const double tot = reduce_slots<false>(d.partials, num_blocks(), sm);
+    if (tid == 0) {
+      st->loc_sum = tot;
+      if (kSingle) st->rr = tot;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------
+// k_scatter_field: compact/laid-out source (or zero) -> compact u and padded copy
+// with ghost images (what the caller's Comm'd initial guess provides,
+// src/solver/proj.ipp:397).
+// ------------------------------------------------------------------------------
+template <int VX>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_scatter_field(const Geom g, const double* __restrict__ src, int64_t s_off, int64_t s_sy,
+                    int64_t s_sz, double* u, double* fpad, double* lo_dst, double* hi_dst) {
+  const Tile t = my_tile<VX>(g);
+  if (!t.active) return;
+  for (int k = t.k0; k < t.k1; ++k) {
+    const int64_t idc = t.i + t.j * g.cy + k * g.cz;
+    const int64_t idp = g.poff + t.i + t.j * g.py + k * g.pz;
+    Vec<VX> val;
+#pragma unroll
+    for (int v = 0; v < VX; ++v)
+      val.v[v] = src ? src[s_off + t.i + v + t.j * s_sy + k * s_sz] : 0.0;
+    if (u) stv<VX>(u + idc, val);
+    stv<VX>(fpad + idp, val);
+    store_images<VX>(g, fpad, idp, t.i, t.j, k, val, lo_dst, hi_dst);
+  }
+  if (lo_dst != nullptr || hi_dst != nullptr) __threadfence_system();
+}
+
+// compact u -> laid-out destination
+__global__ void k_gather_field(const Geom g, const double* __restrict__ u, double* dst,
+                               int64_t d_off, int64_t d_sy, int64_t d_sz) {
+  const int64_t n = g.ncell;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(c % g.nx);
+    const int64_t t = c / g.nx;
+    const int j = (int)(t % g.ny);
+    const int64_t k = t / g.ny;
+    dst[d_off + i + j * d_sy + k * d_sz] = u[c];
+  }
+}
+
+// x += alpha_prev * p : the deferred x update of the last iteration ("iter2", linear.ipp:88)
+template <int VX>
+__global__ void __launch_bounds__(kBX* kBY) k_final_update(const Geom g, const DevPtrs d) {
+  const CgState* st = d.st;
+  const double alpha_prev = st->alpha_prev;
+  const double* __restrict__ p = d.p[st->iter & 1];
+  const Tile t = my_tile<VX>(g);
+  if (!t.active) return;
+  for (int k = t.k0; k < t.k1; ++k) {
+    const int64_t idc = t.i + t.j * g.cy + k * g.cz;
+    const int64_t idp = g.poff + t.i + t.j * g.py + k * g.pz;
+    const Vec<VX> pv = ldv<VX>(p + idp);
+    Vec<VX> uu = ldv<VX>(d.u + idc);
+#pragma unroll
+    for (int v = 0; v < VX; ++v) uu.v[v] = fma(alpha_prev, pv.v[v], uu.v[v]);
+    stv<VX>(d.u + idc, uu);
+  }
+}
+
+// ------------------------------------------------------------------------------
+// AoS rows -> SoA coefficient arrays (one-time transpose at upload).
+// rows: element (cell) index = r_off + i + j*r_sy + k*r_sz, 8 doubles per cell,
+// for planes [k0, k0+nk) of the slab (rows is the base of the chunk: plane k0
+// of the slab is plane 0 of the chunk).
+// ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_rows_to_soa(const Geom g, const double* __restrict__ rows, int64_t r_off, int64_t r_sy,
+                  int64_t r_sz, int k0, int nk, double* a0, double* a1, double* a2, double* a3,
+                  double* a4, double* a5, double* a6, double* rhs) {
+  // one block = 256 consecutive cells of one x-row segment; transpose through smem
+  __shared__ double tile[8][256 + 1];
+  double* outs[8] = {a0, a1, a2, a3, a4, a5, a6, rhs};
+  const int segs = (g.nx + 255) / 256;
+  const int64_t nrow = (int64_t)g.ny * nk;
+  for (int64_t w = blockIdx.x; w < nrow * segs; w += gridDim.x) {
+    const int seg = (int)(w % segs);
+    const int64_t row = w / segs;
+    const int j = (int)(row % g.ny);
+    const int kk = (int)(row / g.ny);
+    const int i0 = seg * 256;
+    const int ncell = min(256, g.nx - i0);
+    const double* src = rows + 8 * (r_off + i0 + j * r_sy + (int64_t)kk * r_sz);
+    __syncthreads();
+    for (int e = threadIdx.x; e < ncell * 8; e += 256) tile[e & 7][e >> 3] = __ldcs(src + e);
+    __syncthreads();
+    const int64_t dst = i0 + j * g.cy + (int64_t)(k0 + kk) * g.cz;
+    for (int q = 0; q < 8; ++q)
+      for (int c = threadIdx.x; c < ncell; c += 256) outs[q][dst + c] = tile[q][c];
+  }
+}
+
+// SoA -> AoS rows (checking the device assembler)
+__global__ void k_soa_to_rows(const Geom g, const DevPtrs d, double* rows) {
+  const int64_t n = g.ncell;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n;
+       c += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int q = 0; q < 7; ++q) rows[8 * c + q] = d.a[q][c];
+    rows[8 * c + 7] = d.rhs[c];
+  }
+}
+
+// ------------------------------------------------------------------------------
+// Point Jacobi twin (linear::SolverJacobi, src/linear/linear.ipp:178-204):
+// u_new = -(e7 + sum_q e[1+q] u[nb_q]) / e0 ; maxdiff = max|u_new - u|.
+// Iterate lives in the padded ping-pong buffers p[0]/p[1].
+// ------------------------------------------------------------------------------
+// stage "check" of SolverJacobi (linear.ipp:195-204)
+__device__ __forceinline__ void jacobi_finish(CgState* st, double* history, double maxdiff) {
+  st->residual = maxdiff;
+  const int it = st->iter + 1;
+  if (it - 1 < st->hist_cap) history[it - 1] = maxdiff;
+  st->iter = it;
+  if (it >= st->miniter && (it > st->maxiter || maxdiff < st->tol)) st->done = 1;
+}
+__global__ void k_finish_jacobi(CgState* st, double* history) {
+  if (st->done) return;
+  jacobi_finish(st, history, st->loc_max);
+}
+
+template <int VX, bool kSingle>
+__global__ void __launch_bounds__(kBX* kBY) k_jacobi(const Geom g, const DevPtrs d) {
+  __shared__ double sm[32];
+  __shared__ int sm_flag;
+  CgState* st = d.st;
+  if (st->done) return;
+  const int par = st->iter & 1;
+  const double* __restrict__ f = d.p[par];
+  double* __restrict__ fn = d.p[par ^ 1];
+  const Tile t = my_tile<VX>(g);
+  double amax = 0.0;
+  if (t.active) {
+    for (int k = t.k0; k < t.k1; ++k) {
+      const int64_t idc = t.i + t.j * g.cy + k * g.cz;
+      const int64_t idp = g.poff + t.i + t.j * g.py + k * g.pz;
+      const Vec<VX> fc = ldv<VX>(f + idp);
+      const double fxm = f[idp - 1], fxp = f[idp + VX];
+      const Vec<VX> fym = ldv<VX>(f + idp - g.py), fyp = ldv<VX>(f + idp + g.py);
+      const Vec<VX> fzm = ldv<VX>(f + idp - g.pz), fzp = ldv<VX>(f + idp + g.pz);
+      Vec<VX> a[7];
+#pragma unroll
+      for (int q = 0; q < 7; ++q) a[q] = ldv_stream<VX>(d.a[q] + idc);
+      const Vec<VX> b = ldv_stream<VX>(d.rhs + idc);
+      Vec<VX> res;
+#pragma unroll
+      for (int v = 0; v < VX; ++v) {
+        const double xm = (v == 0) ? fxm : fc.v[v - 1];
+        const double xp = (v == VX - 1) ? fxp : fc.v[v + 1];
+        double s = b.v[v];
+        s = fma(xm, a[1].v[v], s);
+        s = fma(xp, a[2].v[v], s);
+        s = fma(fym.v[v], a[3].v[v], s);
+        s = fma(fyp.v[v], a[4].v[v], s);
+        s = fma(fzm.v[v], a[5].v[v], s);
+        s = fma(fzp.v[v], a[6].v[v], s);
+        res.v[v] = -s / a[0].v[v];
+        amax = fmax(amax, fabs(res.v[v] - fc.v[v]));
+      }
+      stv<VX>(fn + idp, res);
+      store_images<VX>(g, fn, idp, t.i, t.j, k, res, d.p_lo_dst[par ^ 1], d.p_hi_dst[par ^ 1]);
+    }
+  }
+  if (d.p_lo_dst[0] != nullptr || d.p_hi_dst[0] != nullptr) __threadfence_system();
+  const double bmax = block_reduce<true>(amax, sm);
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  if (tid == 0) d.partials2[block_id()] = bmax;
+  if (last_block(&st->counter_b, num_blocks(), &sm_flag)) {
+    const double mx = reduce_slots<true>(d.partials2, num_blocks(), sm);
+    if (tid == 0) {
+      st->loc_max = mx;
+      if (kSingle) jacobi_finish(st, d.history, mx);
+    }
+  }
+}
+
+// ==============================================================================
+// launch wrappers
+// ==============================================================================
+static dim3 tile_grid(const Geom& g, int vx) {
+  return dim3((g.nx + kBX * vx - 1) / (kBX * vx), (g.ny + kBY - 1) / kBY, (g.nzl + kZC - 1) / kZC);
+}
+
+unsigned tile_blocks(const Geom& g, int vx) {
+  const dim3 gr = tile_grid(g, vx);
+  return gr.x * gr.y * gr.z;
+}
+
+#define APHCG_DISPATCH_VX(vx, ...) \
+  do {                             \
+    if ((vx) == 2) {               \
+      constexpr int VX = 2;        \
+      __VA_ARGS__;                 \
+    } else {                       \
+      constexpr int VX = 1;        \
+      __VA_ARGS__;                 \
+    }                              \
+  } while (0)
+
+void launch_dir_spmv_plain(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s) {
+  const dim3 gr = tile_grid(g, vx), bl(kBX, kBY);
+  APHCG_DISPATCH_VX(vx, {
+    if (single)
+      k_dir_spmv_plain<VX, true><<<gr, bl, 0, s>>>(g, d);
+    else
+      k_dir_spmv_plain<VX, false><<<gr, bl, 0, s>>>(g, d);
+  });
+}
+
+void launch_update(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s) {
+  const dim3 gr = tile_grid(g, vx), bl(kBX, kBY);
+  APHCG_DISPATCH_VX(vx, {
+    if (single)
+      k_update<VX, true><<<gr, bl, 0, s>>>(g, d);
+    else
+      k_update<VX, false><<<gr, bl, 0, s>>>(g, d);
+  });
+}
+
+void launch_finish_dir(const DevPtrs& d, cudaStream_t s) { k_finish_dir<<<1, 1, 0, s>>>(d.st); }
+void launch_finish_upd(const DevPtrs& d, cudaStream_t s) {
+  k_finish_upd<<<1, 1, 0, s>>>(d.st, d.history);
+}
+void launch_finish_init(const DevPtrs& d, cudaStream_t s) { k_finish_init<<<1, 1, 0, s>>>(d.st); }
+void launch_finish_jacobi(const DevPtrs& d, cudaStream_t s) {
+  k_finish_jacobi<<<1, 1, 0, s>>>(d.st, d.history);
+}
+
+void launch_init_residual(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s) {
+  const dim3 gr = tile_grid(g, vx), bl(kBX, kBY);
+  APHCG_DISPATCH_VX(vx, {
+    if (single)
+      k_residual<VX, true, true><<<gr, bl, 0, s>>>(g, d, d.p[1], d.r);
+    else
+      k_residual<VX, true, false><<<gr, bl, 0, s>>>(g, d, d.p[1], d.r);
+  });
+}
+
+void launch_apply(const Geom& g, const DevPtrs& d, int vx, cudaStream_t s) {
+  const dim3 gr = tile_grid(g, vx), bl(kBX, kBY);
+  APHCG_DISPATCH_VX(vx, { (k_residual<VX, false, true><<<gr, bl, 0, s>>>(g, d, d.p[1], d.ap)); });
+}
+
+void launch_scatter_field(const Geom& g, const double* src, int64_t off, int64_t sy, int64_t sz,
+                          double* u, double* fpad, double* lo_dst, double* hi_dst, int vx,
+                          cudaStream_t s) {
+  const dim3 gr = tile_grid(g, vx), bl(kBX, kBY);
+  APHCG_DISPATCH_VX(
+      vx, { (k_scatter_field<VX><<<gr, bl, 0, s>>>(g, src, off, sy, sz, u, fpad, lo_dst, hi_dst)); });
+}
+
+void launch_gather_field(const Geom& g, const double* u, double* dst, int64_t off, int64_t sy,
+                         int64_t sz, cudaStream_t s) {
+  k_gather_field<<<148 * 8, 256, 0, s>>>(g, u, dst, off, sy, sz);
+}
+
+void launch_final_update(const Geom& g, const DevPtrs& d, int vx, cudaStream_t s) {
+  const dim3 gr = tile_grid(g, vx), bl(kBX, kBY);
+  APHCG_DISPATCH_VX(vx, { (k_final_update<VX><<<gr, bl, 0, s>>>(g, d)); });
+}
+
+void launch_rows_to_soa(const Geom& g, const double* rows, int64_t off, int64_t sy, int64_t sz,
+                        int k0, int nk, double* const* a, double* rhs, cudaStream_t s) {
+  k_rows_to_soa<<<148 * 16, 256, 0, s>>>(g, rows, off, sy, sz, k0, nk, a[0], a[1], a[2], a[3],
+                                         a[4], a[5], a[6], rhs);
+}
+
+void launch_soa_to_rows(const Geom& g, const DevPtrs& d, double* rows, cudaStream_t s) {
+  k_soa_to_rows<<<148 * 8, 256, 0, s>>>(g, d, rows);
+}
+
+void launch_jacobi(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s) {
+  const dim3 gr = tile_grid(g, vx), bl(kBX, kBY);
+  APHCG_DISPATCH_VX(vx, {
+    if (single)
+      k_jacobi<VX, true><<<gr, bl, 0, s>>>(g, d);
+    else
+      k_jacobi<VX, false><<<gr, bl, 0, s>>>(g, d);
+  });
+}
+
+}  // namespace acg

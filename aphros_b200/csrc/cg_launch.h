@@ -1,0 +1,48 @@
+// Host-callable launch wrappers of the CG kernels (cg_kernels.cu, cg_spmv_tma.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "cg_types.h"
+
+namespace acg {
+
+// vx: cells per thread along x (2 = 128-bit accesses, needs even nx; else 1).
+// single: this rank is the only one -- the kernel that finishes a reduction also
+// advances the loop state; otherwise an all-reduce and a k_finish_* follow.
+unsigned tile_blocks(const Geom& g, int vx);
+
+void launch_dir_spmv_plain(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s);
+void launch_update(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s);
+void launch_finish_dir(const DevPtrs& d, cudaStream_t s);
+void launch_finish_upd(const DevPtrs& d, cudaStream_t s);
+void launch_finish_init(const DevPtrs& d, cudaStream_t s);
+void launch_finish_jacobi(const DevPtrs& d, cudaStream_t s);
+void launch_init_residual(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s);
+void launch_apply(const Geom& g, const DevPtrs& d, int vx, cudaStream_t s);
+void launch_scatter_field(const Geom& g, const double* src, int64_t off, int64_t sy, int64_t sz,
+                          double* u, double* fpad, double* lo_dst, double* hi_dst, int vx,
+                          cudaStream_t s);
+void launch_gather_field(const Geom& g, const double* u, double* dst, int64_t off, int64_t sy,
+                         int64_t sz, cudaStream_t s);
+void launch_final_update(const Geom& g, const DevPtrs& d, int vx, cudaStream_t s);
+void launch_rows_to_soa(const Geom& g, const double* rows, int64_t off, int64_t sy, int64_t sz,
+                        int k0, int nk, double* const* a, double* rhs, cudaStream_t s);
+void launch_soa_to_rows(const Geom& g, const DevPtrs& d, double* rows, cudaStream_t s);
+void launch_jacobi(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s);
+
+// TMA-staged direction+SpMV kernel (cg_spmv_tma.cu)
+struct TmaPlan;  // opaque: tensor maps + launch geometry
+TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen);
+void tma_plan_destroy(TmaPlan* p);
+unsigned tma_plan_blocks(const TmaPlan* p);
+void launch_dir_spmv_tma(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool single,
+                         cudaStream_t s);
+
+// device-side synthetic assembly (cg_assemble.cu)
+void launch_assemble_spheres(const Geom& g, const DevPtrs& d, double* const* a, double* rhs,
+                             const double* spheres, int nspheres, double rho_in, double rho_out,
+                             double dt, int64_t nz_global, int64_t z0, int nx_g, int ny_g,
+                             const int* periodic, cudaStream_t s);
+
+}  // namespace acg

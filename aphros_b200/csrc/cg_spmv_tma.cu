@@ -1,0 +1,345 @@
+// k_dir_spmv_tma: the direction + SpMV kernel of the CG loop with the p/r
+// planes and their x/y halo staged in shared memory by TMA.
+//
+// Same arithmetic as k_dir_spmv_plain (cg_kernels.cu), i.e. reference stages
+// "iter3" + "iter" (src/linear/linear.ipp:64-101):
+//   x += alpha_prev*p_old ;  p = r + beta*p_old ;  Ap = A p ;  sum p.Ap
+//
+// One CTA owns a TX x TY column of cells and marches through ZC planes of it.
+// For every plane, one elected thread issues two cp.async.bulk.tensor (TMA)
+// loads -- the (TX+4) x (TY+2) boxes of r and p_old, halo included -- into a
+// ring of S stages that complete on an mbarrier; all threads then form p_new
+// for the whole box in shared memory (ring of 4 planes: z-1, z, z+1 and the one
+// being written), store the cells this CTA owns, and evaluate the stencil for
+// the previous plane with every neighbour of p read from shared memory.  The 7
+// coefficient streams and x have no reuse: they go straight from HBM to
+// registers with 128-bit loads issued a whole step ahead of their use.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "cg_kernels.cuh"
+#include "cg_launch.h"
+
+namespace acg {
+
+namespace {
+
+constexpr int TX = 128;      // tile cells along x
+constexpr int TY = 8;        // tile rows
+constexpr int NT = 256;      // threads per CTA
+constexpr int BW = TX + 4;   // box width: x0-2 .. x0+TX+1 (keeps inner pairs 16-byte aligned)
+constexpr int BH = TY + 2;   // box height: y0-1 .. y0+TY
+constexpr int BOX = BW * BH;              // doubles per box
+constexpr int BOXB = (BOX * 8 + 127) / 128 * 128;  // bytes, 128-aligned for TMA
+constexpr int S = 3;         // TMA stages in flight
+constexpr int RING = 4;      // p_new planes kept
+constexpr int kTxBytes = 2 * BOX * 8;
+constexpr int kSmemBytes = S * 2 * BOXB + RING * BOXB + S * 8 + 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <bool kSingle>
+__global__ void __launch_bounds__(NT, 2)
+    k_dir_spmv_tma(const Geom g, const DevPtrs d, const int zc,
+                   const __grid_constant__ CUtensorMap map_r,
+                   const __grid_constant__ CUtensorMap map_p0,
+                   const __grid_constant__ CUtensorMap map_p1) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double sm_red[32];
+  __shared__ int sm_flag;
+  CgState* st = d.st;
+  if (st->done) return;
+  const double beta = cg_beta(st);
+  const double alpha_prev = st->alpha_prev;
+  const int par = st->iter & 1;
+  const CUtensorMap* map_po = par ? &map_p1 : &map_p0;
+  double* __restrict__ pn_glob = d.p[par ^ 1];
+
+  // shared memory carve-up (base is 128-byte aligned by hand: the runtime only
+  // guarantees 16 for dynamic shared memory)
+  unsigned char* base = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  auto stage_r = [&](int s) { return reinterpret_cast<double*>(base + (2 * s) * BOXB); };
+  auto stage_p = [&](int s) { return reinterpret_cast<double*>(base + (2 * s + 1) * BOXB); };
+  auto ring = [&](int s) { return reinterpret_cast<double*>(base + (2 * S + s) * BOXB); };
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (2 * S + RING) * BOXB);
+
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int k0 = blockIdx.z * zc;
+  const int k1 = min(k0 + zc, g.nzl);
+  const int np = k1 - k0 + 2;  // planes k0-1 .. k1
+
+  // TMA coordinates of the box origin (element units of the padded tensor)
+  const int c0 = kGhostX + x0 - 2, c1 = y0;  // row index 1+(y0-1)
+  auto issue = [&](int n) {
+    const int s = n % S;
+    mbar_arrive_expect_tx(&full[s], kTxBytes);
+    tma_load_3d(stage_r(s), &map_r, &full[s], c0, c1, k0 + n);  // plane index 1+(k0-1+n)
+    tma_load_3d(stage_p(s), map_po, &full[s], c0, c1, k0 + n);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int n = 0; n < S && n < np; ++n) issue(n);
+  }
+
+  // cells of this thread: pair (2*lx, 2*lx+1) in rows ly and ly+4 of the tile
+  const int lx = tid & 63, ly = tid >> 6;
+  const int ci = x0 + 2 * lx;
+  const bool act_x = ci < g.nx;
+  bool act[2];
+  int cj[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    cj[h] = y0 + ly + 4 * h;
+    act[h] = act_x && cj[h] < g.ny;
+  }
+  // ownership of box columns/rows for the p_new stores (interior + face ghosts)
+  const int own_xlo = x0 - (x0 == 0 ? 1 : 0);
+  const int own_xhi = min(x0 + TX, g.nx) + (x0 + TX >= g.nx ? 1 : 0);  // exclusive
+  const int own_ylo = y0 - (y0 == 0 ? 1 : 0);
+  const int own_yhi = min(y0 + TY, g.ny) + (y0 + TY >= g.ny ? 1 : 0);
+
+  double acc = 0.0;
+  for (int n = 0; n < np; ++n) {
+    const int z = k0 - 1 + n;  // plane whose p_new is formed in this step
+    const int m = z - 1;       // plane whose stencil is evaluated in this step
+    const bool do_stencil = (n >= 2);
+    const bool z_inner = (z >= k0 && z < k1);
+
+    // -- issue the read-once streams of this step before any waiting ---------------
+    Vec<2> a[2][7];
+    Vec<2> uu[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (do_stencil && act[h]) {
+        const int64_t idc = ci + cj[h] * g.cy + (int64_t)m * g.cz;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) a[h][q] = ldv_stream<2>(d.a[q] + idc);
+      }
+      if (z_inner && act[h]) {
+        uu[h] = ldv_stream<2>(d.u + ci + cj[h] * g.cy + (int64_t)z * g.cz);
+      }
+    }
+
+    const int s = n % S;
+    mbar_wait(&full[s], (n / S) & 1);
+    const double* __restrict__ sr = stage_r(s);
+    const double* __restrict__ sp = stage_p(s);
+    double* __restrict__ rg = ring(n % RING);
+
+    // -- (a) p_new = r + beta*p_old on the whole box; store what this CTA owns --------
+    const bool z_owned = z_inner || (z == -1 && k0 == 0) || (z == g.nzl && k1 == g.nzl);
+    for (int e = tid; e < BOX / 2; e += NT) {
+      const double2 rv = *reinterpret_cast<const double2*>(sr + 2 * e);
+      const double2 pv = *reinterpret_cast<const double2*>(sp + 2 * e);
+      double2 o;
+      o.x = fma(beta, pv.x, rv.x);  // linear.ipp:97-99
+      o.y = fma(beta, pv.y, rv.y);
+      *reinterpret_cast<double2*>(rg + 2 * e) = o;
+      if (z_owned) {
+        const int row = e / (BW / 2), cp = e - row * (BW / 2);
+        const int y = y0 - 1 + row, x = x0 - 2 + 2 * cp;
+        if (y >= own_ylo && y < own_yhi) {
+          const bool in0 = (x >= own_xlo && x < own_xhi);
+          const bool in1 = (x + 1 >= own_xlo && x + 1 < own_xhi);
+          double* dst = pn_glob + g.poff + x + (int64_t)y * g.py + (int64_t)z * g.pz;
+          if (in0 && in1) {
+            *reinterpret_cast<double2*>(dst) = o;
+          } else if (in0) {
+            dst[0] = o.x;
+          } else if (in1) {
+            dst[1] = o.y;
+          }
+        }
+      }
+    }
+    // -- (b) deferred x update (linear.ipp:88) with p_old of the own cells -------------
+    if (z_inner) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (act[h]) {
+          const int o = (ly + 4 * h + 1) * BW + 2 + 2 * lx;
+          const double2 pv = *reinterpret_cast<const double2*>(sp + o);
+          uu[h].v[0] = fma(alpha_prev, pv.x, uu[h].v[0]);
+          uu[h].v[1] = fma(alpha_prev, pv.y, uu[h].v[1]);
+          stv_stream<2>(d.u + ci + cj[h] * g.cy + (int64_t)z * g.cz, uu[h]);
+        }
+      }
+    }
+    __syncthreads();  // p_new(z) visible; stage s fully consumed
+    if (tid == 0 && n + S < np) issue(n + S);
+
+    // -- (d) stencil of plane m = z-1 from the ring -------------------------------------
+    if (do_stencil) {
+      const double* __restrict__ rc = ring((n + RING - 1) % RING);  // plane m
+      const double* __restrict__ rm = ring((n + RING - 2) % RING);  // plane m-1
+      const double* __restrict__ rp = rg;                            // plane m+1
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (act[h]) {
+          const int o = (ly + 4 * h + 1) * BW + 2 + 2 * lx;
+          const double2 pc = *reinterpret_cast<const double2*>(rc + o);
+          const double pxm = rc[o - 1], pxp = rc[o + 2];
+          const double2 pym = *reinterpret_cast<const double2*>(rc + o - BW);
+          const double2 pyp = *reinterpret_cast<const double2*>(rc + o + BW);
+          const double2 pzm = *reinterpret_cast<const double2*>(rm + o);
+          const double2 pzp = *reinterpret_cast<const double2*>(rp + o);
+          Vec<2> ap;
+          // accumulation order of the reference: centre, then q = 0..5 (linear.ipp:67-70)
+          double t = pc.x * a[h][0].v[0];
+          t = fma(pxm, a[h][1].v[0], t);
+          t = fma(pc.y, a[h][2].v[0], t);
+          t = fma(pym.x, a[h][3].v[0], t);
+          t = fma(pyp.x, a[h][4].v[0], t);
+          t = fma(pzm.x, a[h][5].v[0], t);
+          t = fma(pzp.x, a[h][6].v[0], t);
+          ap.v[0] = t;
+          acc = fma(pc.x, t, acc);
+          t = pc.y * a[h][0].v[1];
+          t = fma(pc.x, a[h][1].v[1], t);
+          t = fma(pxp, a[h][2].v[1], t);
+          t = fma(pym.y, a[h][3].v[1], t);
+          t = fma(pyp.y, a[h][4].v[1], t);
+          t = fma(pzm.y, a[h][5].v[1], t);
+          t = fma(pzp.y, a[h][6].v[1], t);
+          ap.v[1] = t;
+          acc = fma(pc.y, t, acc);
+          stv_stream<2>(d.ap + ci + cj[h] * g.cy + (int64_t)m * g.cz, ap);
+        }
+      }
+    }
+  }
+
+  const double bsum = block_reduce<false>(acc, sm_red);
+  const unsigned nblk = gridDim.x * gridDim.y * gridDim.z;
+  const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (tid == 0) d.partials[bid] = bsum;
+  if (last_block(&st->counter_a, nblk, &sm_flag)) {
+    const double tot = reduce_slots<false>(d.partials, nblk, sm_red);
+    if (tid == 0) {
+      st->loc_sum = tot;
+      if (kSingle) cg_finish_dir(st, tot);
+    }
+  }
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                              const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct TmaPlan {
+  alignas(64) CUtensorMap map_r, map_p0, map_p1;
+  dim3 grid;
+  int zc;
+};
+
+TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen) {
+  auto fail = [&](const char* msg) -> TmaPlan* {
+    if (err && errlen > 0) snprintf(err, errlen, "%s", msg);
+    return nullptr;
+  };
+  if (g.nx % 2) return fail("nx is odd");
+  EncodeFn encode = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault,
+                              &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !encode) {
+    cudaGetLastError();
+    return fail("cuTensorMapEncodeTiled not available");
+  }
+  TmaPlan* p = new TmaPlan();
+  const cuuint64_t gdim[3] = {(cuuint64_t)g.py, (cuuint64_t)(g.ny + 2), (cuuint64_t)(g.nzl + 2)};
+  const cuuint64_t gstr[2] = {(cuuint64_t)g.py * 8, (cuuint64_t)g.pz * 8};
+  const cuuint32_t box[3] = {BW, BH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  double* bases[3] = {d.r, d.p[0], d.p[1]};
+  CUtensorMap* maps[3] = {&p->map_r, &p->map_p0, &p->map_p1};
+  for (int i = 0; i < 3; ++i) {
+    const CUresult rc = encode(maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, bases[i], gdim, gstr,
+                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+      delete p;
+      char msg[96];
+      snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (CUresult %d)", (int)rc);
+      return fail(msg);
+    }
+  }
+  // planes per CTA: enough CTAs for a few waves of 2 CTAs/SM, but long columns
+  const int tiles = ((g.nx + TX - 1) / TX) * ((g.ny + TY - 1) / TY);
+  int zc = 32;
+  const char* env = getenv("APHCG_ZC");
+  if (env) zc = atoi(env);
+  while (zc > 4 && (int64_t)tiles * ((g.nzl + zc - 1) / zc) < 148 * 2 * 4) zc /= 2;
+  if (zc < 1) zc = 1;
+  if (zc > g.nzl) zc = g.nzl;
+  p->zc = zc;
+  p->grid = dim3((g.nx + TX - 1) / TX, (g.ny + TY - 1) / TY, (g.nzl + zc - 1) / zc);
+  if (cudaFuncSetAttribute(k_dir_spmv_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           kSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(k_dir_spmv_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           kSmemBytes) != cudaSuccess) {
+    cudaGetLastError();
+    delete p;
+    return fail("cannot raise the dynamic shared memory limit");
+  }
+  return p;
+}
+
+void tma_plan_destroy(TmaPlan* p) { delete p; }
+unsigned tma_plan_blocks(const TmaPlan* p) { return p->grid.x * p->grid.y * p->grid.z; }
+
+void launch_dir_spmv_tma(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool single,
+                         cudaStream_t s) {
+  if (single) {
+    k_dir_spmv_tma<true><<<p->grid, NT, kSmemBytes, s>>>(g, d, p->zc, p->map_r, p->map_p0,
+                                                         p->map_p1);
+  } else {
+    k_dir_spmv_tma<false><<<p->grid, NT, kSmemBytes, s>>>(g, d, p->zc, p->map_r, p->map_p0,
+                                                          p->map_p1);
+  }
+}
+
+}  // namespace acg

@@ -1,0 +1,74 @@
+// Shared host/device types of the CG solver (libaphcg.so).
+#pragma once
+
+#include <cstdint>
+
+namespace acg {
+
+// Ghost offset of inner cell i=0 inside a padded row: keeps inner rows 128-byte
+// aligned so that pair (128-bit) accesses and TMA boxes start on line boundaries.
+constexpr int kGhostX = 16;
+
+// Geometry of one rank's z-slab.
+//
+// "compact" arrays (coefficients, rhs, u, Ap) hold inner cells only:
+//   idx = i + j*cy + k*cz.
+// "padded" arrays (r, p0, p1) carry one ghost layer on each of the six faces
+// (what m.Comm(&f, direct_one) maintains in the reference,
+// src/linear/linear.ipp:57,100):
+//   idx = poff + i + j*py + k*pz,  i in [-1,nx], j in [-1,ny], k in [-1,nzl].
+struct Geom {
+  int nx, ny, nzl;
+  int per_x, per_y;     // periodic in x / y (wrap inside the slab)
+  int64_t cy, cz, ncell;
+  int64_t py, pz, poff, ptotal;
+};
+
+// Loop state; lives in device memory, updated by the kernels themselves so the
+// host never has to read a scalar inside the loop (reference stages
+// "iter2"/"iter3"/"check", src/linear/linear.ipp:83-114).
+struct CgState {
+  // all-reduced scalars
+  double rr;        // sum r^2 of the current residual   (dot_r / next dot_r_prev)
+  double rr_prev;   // sum r^2 before the last update     (dot_r_prev)
+  double pAp;       // sum p*Ap                           (dot_p_lp)
+  double max_r;     // max |r|
+  double alpha_prev;  // alpha of the last completed iteration (x update is deferred
+                      // into the next direction kernel)
+  double residual;
+  // this rank's partial results, all-reduced in place when nranks > 1
+  double loc_sum;
+  double loc_max;
+  // Conf (src/linear/linear.h:21-25) + Extra::residual_max
+  double tol;
+  double cell_volume;
+  int miniter, maxiter, maxnorm;
+  int iter;      // completed iterations
+  int done;      // exit rule fired (linear.ipp:110-113); later kernels return at once
+  int hist_cap;
+  unsigned counter_a, counter_b;  // last-block-done tickets
+  int pad;
+};
+
+struct DevPtrs {
+  const double* a[7];   // SoA coefficients [c,x-,x+,y-,y+,z-,z+], compact
+  const double* rhs;    // e7, compact
+  double* u;            // iterate, compact
+  double* ap;           // A*p, compact
+  double* r;            // residual, padded
+  double* p[2];         // search direction, padded, ping-pong by iteration parity
+  // where this slab's bottom / top inner plane of a padded field must also be
+  // stored: the neighbour's ghost plane (peer memory over NVLink when the
+  // neighbour is another GPU, own ghost plane when the slab wraps onto itself).
+  // Each points at element (i=0, j=0) of the destination plane.
+  double* r_lo_dst;     // destination of inner plane k=0      (or nullptr)
+  double* r_hi_dst;     // destination of inner plane k=nzl-1  (or nullptr)
+  double* p_lo_dst[2];  // same for p[0], p[1] (initial guess copy, Jacobi iterate)
+  double* p_hi_dst[2];
+  CgState* st;
+  double* history;
+  double* partials;     // one slot per block for sums
+  double* partials2;    // one slot per block for max
+};
+
+}  // namespace acg

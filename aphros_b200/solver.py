@@ -1,0 +1,324 @@
+"""Host-side mirror of the reference's linear-solver interface over libaphcg.so.
+
+Names, argument meaning and error behaviour follow the reference so that the
+parity tests read like its own (src/test/linear/main.cpp):
+
+  linear::Solver<M>            -> Solver          (Conf, Info, Solve, SetConf, GetConf;
+                                                   src/linear/linear.h:15-57)
+  linear::ModuleLinear<M>      -> ModuleLinear    (GetInstance(name).Make(var, prefix, m),
+                                                   GetConf(var, prefix); linear.h:59-76)
+  module "conjugate_cuda"      -> SolverConjugateCuda  (sibling of "conjugate",
+                                                   src/linear/linear.ipp:239-253)
+  module "jacobi_cuda"         -> SolverJacobiCuda     (sibling of "jacobi")
+
+The real drop-in for aphros itself is the C++ adapter
+aphros_b200/plugin/linear_conjugate_cuda.cpp; this module is the same thing for
+Python callers (tests, bench).  All arithmetic happens in the CUDA library; a
+missing library or GPU raises, it never falls back to the CPU.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+
+
+@dataclass
+class Conf:
+    """linear::Solver<M>::Conf (src/linear/linear.h:21-25)."""
+    tol: float = 0.0
+    miniter: int = 1
+    maxiter: int = 100
+
+
+@dataclass
+class Info:
+    """linear::Solver<M>::Info (src/linear/linear.h:27-30) + device timings."""
+    residual: float = 0.0
+    iter: int = 0
+    loop_ms: float = 0.0
+    total_ms: float = 0.0
+
+
+@dataclass
+class Mesh:
+    """What the solver reads from MeshCartesian (src/geom/mesh.h): global size,
+    periodicity flags (m.flags.is_periodic) and cell volume, plus the z-slab of
+    this rank when the domain is split over several GPUs."""
+    shape: tuple  # (nz, ny, nx) global inner cells
+    periodic: tuple = (True, True, True)  # (x, y, z)
+    cell_volume: float | None = None
+    rank: int = 0
+    nranks: int = 1
+    z0: int = 0
+    nz_local: int | None = None
+    device: int = 0
+
+    def __post_init__(self):
+        if self.cell_volume is None:
+            self.cell_volume = (1.0 / max(self.shape)) ** 3
+        if self.nz_local is None:
+            self.nz_local = self.shape[0]
+
+    @property
+    def local_shape(self):
+        return (self.nz_local, self.shape[1], self.shape[2])
+
+
+class Solver:
+    """Abstract linear::Solver<M> (src/linear/linear.h:15-57)."""
+
+    def __init__(self, conf: Conf):
+        self.conf = conf
+
+    def Solve(self, fc_system, fc_init, fc_sol):
+        raise NotImplementedError
+
+    def SetConf(self, c: Conf):
+        self.conf = c
+
+    def GetConf(self) -> Conf:
+        return self.conf
+
+
+class _CudaSolverBase(Solver):
+    _method = "conjugate"
+
+    def __init__(self, conf: Conf, extra: dict | None, m: Mesh, flags: int = 0):
+        super().__init__(conf)
+        extra = extra or {}
+        self.mesh = m
+        nz, ny, nx = m.shape
+        d = capi.Desc()
+        d.nx, d.ny, d.nz = nx, ny, nz
+        d.periodic[:] = [int(bool(p)) for p in m.periodic]
+        d.cell_volume = m.cell_volume
+        d.device = m.device
+        d.rank, d.nranks = m.rank, m.nranks
+        d.z0, d.nz_local = m.z0, m.nz_local
+        d.flags = flags | (capi.APHCG_MAXNORM if extra.get("residual_max") else 0)
+        self._h = ctypes.c_void_p()
+        capi.check(capi.lib().aphcg_create(ctypes.byref(self._h), ctypes.byref(d)))
+
+    # -- lifetime ---------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            capi.lib().aphcg_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ------------------------------------------------------------------
+    def _conf(self):
+        return capi.Conf(float(self.conf.tol), int(self.conf.miniter), int(self.conf.maxiter))
+
+    def _check_field(self, a, rows):
+        want = self.mesh.local_shape + ((8,) if rows else ())
+        if a.dtype != np.float64 or tuple(a.shape) != want:
+            raise ValueError("expected float64 array of shape %s, got %s %s"
+                             % (want, a.dtype, a.shape))
+
+    def _run(self):
+        info = capi.Info()
+        c = self._conf()
+        fn = capi.lib().aphcg_run if self._method == "conjugate" else capi.lib().aphcg_run_jacobi
+        capi.check(fn(self._h, ctypes.byref(c), ctypes.byref(info)))
+        return Info(info.residual, info.iter, info.loop_ms, info.total_ms)
+
+    # -- linear::Solver<M>::Solve ---------------------------------------------------
+    def Solve(self, fc_system, fc_init, fc_sol):
+        """fc_system: (nz_local, ny, nx, 8) rows [c,x-,x+,y-,y+,z-,z+,const];
+        fc_init: initial guess, may be fc_sol itself, None = zero guess
+        (src/linear/linear.h:34-44); fc_sol: output array.  Arrays may be strided
+        views (e.g. the inner part of a field with halos).  Returns Info."""
+        L = capi.lib()
+        ls = self.mesh.local_shape
+        self._check_field(fc_system, True)
+        self._check_field(fc_sol, False)
+        lay_s = capi.layout_of(fc_system, ls, 8)
+        lay_x = capi.layout_of(fc_sol, ls)
+        if self._method != "conjugate":
+            capi.check(L.aphcg_upload_system(self._h, capi.ptr(fc_system), ctypes.byref(lay_s)))
+            self._upload_guess(fc_init)
+            info = self._run()
+            capi.check(L.aphcg_download_solution(self._h, capi.ptr(fc_sol), ctypes.byref(lay_x)))
+            return info
+        info = capi.Info()
+        c = self._conf()
+        if fc_init is not None:
+            self._check_field(fc_init, False)
+            lay_0 = capi.layout_of(fc_init, ls)
+            p0, pl0 = capi.ptr(fc_init), ctypes.byref(lay_0)
+        else:
+            p0, pl0 = None, None
+        capi.check(L.aphcg_solve(self._h, capi.ptr(fc_system), ctypes.byref(lay_s), p0, pl0,
+                                 capi.ptr(fc_sol), ctypes.byref(lay_x), ctypes.byref(c),
+                                 ctypes.byref(info)))
+        return Info(info.residual, info.iter, info.loop_ms, info.total_ms)
+
+    # -- device-resident pieces (bench, tests) ----------------------------------------
+    def _upload_guess(self, fc_init):
+        if fc_init is None:
+            capi.check(capi.lib().aphcg_upload_guess(self._h, None, None))
+        else:
+            self._check_field(fc_init, False)
+            lay = capi.layout_of(fc_init, self.mesh.local_shape)
+            capi.check(capi.lib().aphcg_upload_guess(self._h, capi.ptr(fc_init), ctypes.byref(lay)))
+
+    def UploadSystem(self, fc_system):
+        self._check_field(fc_system, True)
+        lay = capi.layout_of(fc_system, self.mesh.local_shape, 8)
+        capi.check(capi.lib().aphcg_upload_system(self._h, capi.ptr(fc_system), ctypes.byref(lay)))
+
+    def UploadGuess(self, fc_init):
+        self._upload_guess(fc_init)
+
+    def Run(self) -> Info:
+        return self._run()
+
+    def DownloadSolution(self, fc_sol):
+        self._check_field(fc_sol, False)
+        lay = capi.layout_of(fc_sol, self.mesh.local_shape)
+        capi.check(capi.lib().aphcg_download_solution(self._h, capi.ptr(fc_sol), ctypes.byref(lay)))
+        return fc_sol
+
+    def History(self, n=None):
+        n = int(n if n is not None else self.conf.maxiter + 2)
+        out = np.zeros(max(n, 1), dtype=np.float64)
+        got = capi.check(capi.lib().aphcg_get_history(self._h, capi.ptr(out), n))
+        return out[:got]
+
+    def Apply(self, v):
+        """A*v for the resident system (stage "iter" operator, linear.ipp:65-72)."""
+        self._check_field(v, False)
+        out = np.empty(self.mesh.local_shape, dtype=np.float64)
+        lv = capi.layout_of(v, self.mesh.local_shape)
+        capi.check(capi.lib().aphcg_apply(self._h, capi.ptr(v), ctypes.byref(lv), capi.ptr(out), None))
+        return out
+
+    def AssembleSpheres(self, spheres, rho_in=1e-3, rho_out=1.0, dt=1e-3):
+        sph = np.ascontiguousarray(spheres, dtype=np.float64).reshape(-1, 4)
+        capi.check(capi.lib().aphcg_assemble_spheres(self._h, capi.ptr(sph), sph.shape[0],
+                                                     rho_in, rho_out, dt))
+
+    def DownloadSystem(self):
+        out = np.empty(self.mesh.local_shape + (8,), dtype=np.float64)
+        capi.check(capi.lib().aphcg_download_system(self._h, capi.ptr(out), None))
+        return out
+
+    def TimerStart(self):
+        capi.check(capi.lib().aphcg_timer_start(self._h))
+
+    def TimerStop(self) -> float:
+        ms = ctypes.c_double()
+        capi.check(capi.lib().aphcg_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def ProfileKernels(self, iters=20):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        capi.check(capi.lib().aphcg_profile_kernels(self._h, iters, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def LaunchCount(self):
+        return int(capi.lib().aphcg_launch_count(self._h))
+
+    def LaunchesPerIter(self):
+        return int(capi.lib().aphcg_launches_per_iter(self._h))
+
+    # -- multi-GPU wiring (see aphros_b200/distr.py) -----------------------------------
+    def CommInit(self, unique_id: bytes):
+        buf = ctypes.create_string_buffer(bytes(unique_id), capi.UNIQUE_ID_BYTES)
+        capi.check(capi.lib().aphcg_comm_init(self._h, buf))
+
+    def IpcExport(self) -> bytes:
+        buf = ctypes.create_string_buffer(capi.IPC_BYTES)
+        capi.check(capi.lib().aphcg_ipc_export(self._h, buf))
+        return buf.raw
+
+    def IpcConnect(self, lo_blob, hi_blob):
+        lo = ctypes.create_string_buffer(bytes(lo_blob), capi.IPC_BYTES) if lo_blob else None
+        hi = ctypes.create_string_buffer(bytes(hi_blob), capi.IPC_BYTES) if hi_blob else None
+        capi.check(capi.lib().aphcg_ipc_connect(self._h, lo, hi))
+
+
+class SolverConjugateCuda(_CudaSolverBase):
+    """B200 sibling of linear::SolverConjugate (src/linear/linear.h:78-100):
+    unpreconditioned CG with the reference's recurrence, constants and exit rule
+    (src/linear/linear.ipp:42-125)."""
+    _method = "conjugate"
+
+
+class SolverJacobiCuda(_CudaSolverBase):
+    """B200 sibling of linear::SolverJacobi (src/linear/linear.ipp:152-237)."""
+    _method = "jacobi"
+
+
+class ModuleLinear:
+    """linear::ModuleLinear<M> registry (src/linear/linear.h:59-76,
+    src/util/module.h:21-85)."""
+    _instances: dict = {}
+
+    def __init__(self, name):
+        self.name = name
+
+    @classmethod
+    def Register(cls, mod):
+        if mod.name in cls._instances:
+            raise RuntimeError("RegisterModule: module '%s' already registered" % mod.name)
+        cls._instances[mod.name] = mod
+        return True
+
+    @classmethod
+    def GetInstance(cls, name):
+        return cls._instances.get(name)
+
+    @classmethod
+    def GetInstances(cls):
+        return dict(cls._instances)
+
+    @staticmethod
+    def GetConf(var: dict, prefix: str) -> Conf:
+        # keys are hypre_<prefix>_* even for non-hypre modules (linear.h:66-75);
+        # tol and maxiter are mandatory (Vars::operator[] throws), miniter defaults to 0
+        p = "hypre_" + prefix + "_"
+        return Conf(tol=float(var[p + "tol"]), maxiter=int(var[p + "maxiter"]),
+                    miniter=int(var.get(p + "miniter", 0)))
+
+    def Make(self, var: dict, prefix: str, m: Mesh) -> Solver:
+        raise NotImplementedError
+
+
+class ModuleLinearConjugateCuda(ModuleLinear):
+    def __init__(self):
+        super().__init__("conjugate_cuda")
+
+    def Make(self, var, prefix, m):
+        # extras follow the "linsolver_<prefix>_<key>" convention (linear.ipp:245-249);
+        # read with a default: Vars["k"] throws on a missing key
+        extra = {"residual_max": bool(int(var.get("linsolver_" + prefix + "_maxnorm", 0)))}
+        flags = 0
+        if int(var.get("linsolver_" + prefix + "_cuda_graph", 1)) == 0:
+            flags |= capi.APHCG_NO_GRAPH
+        if int(var.get("linsolver_" + prefix + "_cuda_tma", 1)) == 0:
+            flags |= capi.APHCG_NO_TMA
+        return SolverConjugateCuda(self.GetConf(var, prefix), extra, m, flags)
+
+
+class ModuleLinearJacobiCuda(ModuleLinear):
+    def __init__(self):
+        super().__init__("jacobi_cuda")
+
+    def Make(self, var, prefix, m):
+        return SolverJacobiCuda(self.GetConf(var, prefix), {}, m, 0)
+
+
+_kReg = [ModuleLinear.Register(ModuleLinearConjugateCuda()),
+         ModuleLinear.Register(ModuleLinearJacobiCuda())]

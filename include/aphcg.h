@@ -1,0 +1,184 @@
+/* aphcg -- B200-native conjugate-gradient solver for aphros' 7-point
+ * FieldCell<Expr> pressure systems.  C ABI of libaphcg.so.
+ *
+ * This is the drop-in boundary: everything the reference's
+ *   linear::Solver<M>::Solve / SetConf / GetConf      (src/linear/linear.h:15-57)
+ *   linear::ModuleLinear<M>::Make                      (src/linear/linear.h:59-76)
+ * needs from a device module, as plain pointers and sizes.  The aphros-side
+ * adapter that binds it (ModuleLinear "conjugate_cuda") is
+ * aphros_b200/plugin/linear_conjugate_cuda.cpp; INTEGRATION.md shows the wiring.
+ *
+ * The product path is CUDA (sm_100a) only: every compute entry point fails with
+ * APHCG_ERR_CUDA when no device is usable.  There is no CPU fallback.
+ *
+ * Conventions
+ *   - cells are indexed x fastest, then y, then z (src/geom/block.h:149-158);
+ *   - a system row is 8 doubles [c, x-, x+, y-, y+, z-, z+, const] meaning
+ *       e0*x[c] + sum_q e[1+q]*x[nb_q(c)] + e7 = 0
+ *     (src/geom/mesh.h:484-485, src/linear/linear.h:34-44);
+ *   - all functions return 0 on success, a negative APHCG_ERR_* otherwise, and
+ *     leave a message for aphcg_last_error() (thread local).
+ */
+#ifndef APHCG_H_
+#define APHCG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APHCG_VERSION 1
+
+enum {
+  APHCG_OK = 0,
+  APHCG_ERR_ARG = -1,    /* bad argument */
+  APHCG_ERR_CUDA = -2,   /* CUDA runtime/driver error, or no device */
+  APHCG_ERR_COMM = -3,   /* NCCL / peer-memory error */
+  APHCG_ERR_STATE = -4   /* call order (e.g. run before upload) */
+};
+
+/* aphcg_desc.flags */
+enum {
+  APHCG_MAXNORM = 1u << 0,   /* residual = max|r|/V  (Extra::residual_max,
+                                src/linear/linear.ipp:103-107,245-249) */
+  APHCG_NO_GRAPH = 1u << 1,  /* launch kernels one by one instead of replaying
+                                a CUDA graph (debugging) */
+  APHCG_NO_TMA = 1u << 2     /* use the plain-load stencil kernel instead of the
+                                TMA-staged one (debugging / comparison) */
+};
+
+typedef struct aphcg aphcg_t;
+
+/* Geometry of the solve.  The domain is cut into z-slabs, one per rank (one
+ * rank = one GPU = one process); rank r owns the contiguous planes
+ * [z0, z0+nz_local).  nranks == 1: z0 = 0, nz_local = nz. */
+typedef struct {
+  int64_t nx, ny, nz;    /* global inner cells */
+  int32_t periodic[3];   /* m.flags.is_periodic (src/distr/distr.ipp:55-59); a
+                            neighbour outside a non-periodic boundary contributes
+                            the value 0 (every reference assembler zeroes that
+                            coefficient) */
+  double cell_volume;    /* m.GetCellSize().prod() (src/geom/mesh.h:171-173) */
+  int32_t device;        /* CUDA device ordinal of this rank */
+  int32_t rank, nranks;
+  int64_t z0, nz_local;
+  uint32_t flags;
+} aphcg_desc;
+
+/* Where inner cell (i,j,k) of THIS RANK'S slab lives in a caller array:
+ * element index = offset + i + j*stride_y + k*stride_z (elements are doubles
+ * for scalar fields, 8-double rows for the system).  A compact slab is
+ * {0, nx, nx*ny}; a reference FieldCell with halos (src/geom/mesh.ipp:60-113)
+ * is {hl*(1+sy+sz), nx+2*hl+1, sy*(ny+2*hl+1)}.  NULL layout = compact. */
+typedef struct {
+  int64_t offset, stride_y, stride_z;
+} aphcg_layout;
+
+/* linear::Solver<M>::Conf (src/linear/linear.h:21-25) */
+typedef struct {
+  double tol;
+  int32_t miniter;
+  int32_t maxiter;
+} aphcg_conf;
+
+/* linear::Solver<M>::Info (src/linear/linear.h:27-30) plus timings */
+typedef struct {
+  double residual;
+  int32_t iter;
+  int32_t reserved;
+  double loop_ms;      /* device time of the CG loop alone (CUDA events) */
+  double total_ms;     /* device time of everything the call enqueued */
+} aphcg_info;
+
+const char* aphcg_last_error(void);
+int aphcg_version(void);
+/* number of usable CUDA devices (0 if none); never fails */
+int aphcg_device_count(void);
+
+int aphcg_create(aphcg_t** out, const aphcg_desc* desc);
+int aphcg_destroy(aphcg_t* h);
+
+/* Pinned host memory for callers that stage fields themselves (the adapter's
+ * rank-wide shared fields): host<->device copies from it run at full link speed. */
+int aphcg_host_alloc(void** out, uint64_t bytes);
+int aphcg_host_free(void* p);
+
+/* ---- one call = one linear::Solver::Solve (host buffers in, host buffer out) --
+ * system: rows of this rank's slab; x0: initial guess or NULL (zero guess,
+ * linear.ipp:43-47); x: solution out (may alias x0, linear.h:40). */
+int aphcg_solve(
+    aphcg_t* h, const double* system, const aphcg_layout* system_layout,
+    const double* x0, const aphcg_layout* x0_layout, double* x,
+    const aphcg_layout* x_layout, const aphcg_conf* conf, aphcg_info* info);
+
+/* ---- the same, split so that fields can stay resident in HBM ---------------- */
+int aphcg_upload_system(aphcg_t* h, const double* system, const aphcg_layout* layout);
+int aphcg_upload_guess(aphcg_t* h, const double* x0, const aphcg_layout* layout);
+/* device-resident inputs (device pointers; same row/field formats) */
+int aphcg_set_system_device(aphcg_t* h, const double* d_system, const aphcg_layout* layout);
+int aphcg_set_guess_device(aphcg_t* h, const double* d_x0, const aphcg_layout* layout);
+/* initial residual + CG loop + final update of x; fields stay on the device */
+int aphcg_run(aphcg_t* h, const aphcg_conf* conf, aphcg_info* info);
+int aphcg_download_solution(aphcg_t* h, double* x, const aphcg_layout* layout);
+int aphcg_get_solution_device(aphcg_t* h, double* d_x, const aphcg_layout* layout);
+/* residual after each completed iteration of the last run (n <= iter) */
+int aphcg_get_history(aphcg_t* h, double* out, int32_t n);
+
+/* SolverJacobi twin (src/linear/linear.ipp:152-237) on the same resident system */
+int aphcg_run_jacobi(aphcg_t* h, const aphcg_conf* conf, aphcg_info* info);
+
+/* out = A*v for the resident system (host v/out, slab-local, compact or laid
+ * out): the stage-"iter" operator alone, for operator-level parity tests. */
+int aphcg_apply(aphcg_t* h, const double* v, const aphcg_layout* v_layout,
+                double* out, const aphcg_layout* out_layout);
+
+/* Synthetic variable-density projection system assembled on the device from a
+ * sphere list (formulas of src/solver/proj.ipp:343-398):
+ * spheres = nspheres x {cx,cy,cz,r}.  Replaces upload_system for benchmarks
+ * whose system would not fit comfortably in host memory. */
+int aphcg_assemble_spheres(
+    aphcg_t* h, const double* spheres, int32_t nspheres, double rho_in,
+    double rho_out, double dt);
+/* copy the resident system back as rows (for checking the assembler) */
+int aphcg_download_system(aphcg_t* h, double* system, const aphcg_layout* layout);
+
+/* ---- multi-GPU (nranks > 1): one process per GPU -------------------------------
+ * Scalars are all-reduced with NCCL; residual halo planes are written straight
+ * into the neighbour's ghost planes over NVLink (peer memory), so the two
+ * neighbours' buffers must be opened once after create:
+ *   1. rank 0: aphcg_comm_unique_id(id); broadcast id to all ranks (the host
+ *      harness does this with torch.distributed / MPI / a file);
+ *   2. every rank: aphcg_comm_init(h, id)              (collective)
+ *   3. every rank: aphcg_ipc_export(h, mine); all-gather the 64-byte blobs;
+ *   4. every rank: aphcg_ipc_connect(h, blob[lo], blob[hi])
+ *      (lo/hi = neighbour ranks in z; NULL where there is none). */
+#define APHCG_UNIQUE_ID_BYTES 128
+#define APHCG_IPC_BYTES 128
+int aphcg_comm_unique_id(void* id_out);
+int aphcg_comm_init(aphcg_t* h, const void* id);
+int aphcg_ipc_export(aphcg_t* h, void* blob_out);
+int aphcg_ipc_connect(aphcg_t* h, const void* lo_blob, const void* hi_blob);
+
+/* Device-side timing on the handle's stream (CUDA events): start records an
+ * event; stop records another, waits for it and returns the milliseconds between. */
+int aphcg_timer_start(aphcg_t* h);
+int aphcg_timer_stop(aphcg_t* h, double* ms);
+/* Per-kernel timing of the loop on the resident system: restarts from the
+ * resident guess, runs `iters` iterations launched one by one with an event
+ * around every kernel, and returns the average duration of the direction+SpMV
+ * kernel and of the update kernel (milliseconds).  Leaves no valid solution. */
+int aphcg_profile_kernels(aphcg_t* h, int32_t iters, double* ms_dir_spmv, double* ms_update);
+
+/* cudaStream_t the handle enqueues on (as void*), for callers that time with
+ * their own events */
+void* aphcg_stream(aphcg_t* h);
+/* number of kernels this handle has launched so far (graph replays counted per node) */
+int64_t aphcg_launch_count(aphcg_t* h);
+/* number of kernel launches per CG iteration of the current configuration */
+int aphcg_launches_per_iter(aphcg_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APHCG_H_ */

@@ -1,0 +1,37 @@
+"""Shared parity cases: small systems the CPU oracle finishes in seconds."""
+
+from __future__ import annotations
+
+import numpy as np
+
+from aphros_b200 import systems
+
+
+def case_tlinear(n=32, rho_in=10.0, shape=None):
+    s, exact = systems.tlinear_system(n, rho_in=rho_in, shape=shape)
+    return dict(system=s, periodic=(True, True, True), exact=exact)
+
+
+def case_density(n=32, nspheres=8, seed=7, periodic=(False, False, False), shape=None,
+                 rho_in=1e-3):
+    s, _ = systems.density_poisson_system(n, nspheres=nspheres, seed=seed, periodic=periodic,
+                                          shape=shape, rho_in=rho_in)
+    return dict(system=s, periodic=periodic)
+
+
+def case_periodic_const(n=32, shape=None):
+    s, exact = systems.periodic_constant_system(n, shape=shape)
+    return dict(system=s, periodic=(True, True, True), exact=exact)
+
+
+def random_guess(shape, seed=3):
+    return np.random.default_rng(seed).standard_normal(shape)
+
+
+def rel_max_abs(a, b):
+    """The parity measure of the north star: max|a-b| / max|b|."""
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def remove_mean(a):
+    return a - a.mean()

@@ -1,0 +1,237 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the
+same inputs.  Floating point: solution within 1e-10 relative max-abs of the
+oracle's, iteration count within +-2 (the north star's tolerance)."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from aphros_b200 import Conf, Mesh, SolverConjugateCuda, SolverJacobiCuda, capi
+from cases import (case_density, case_periodic_const, case_tlinear, random_guess, rel_max_abs,
+                   remove_mean)
+
+pytestmark = pytest.mark.gpu
+
+X_TOL = 1e-10   # relative max-abs error of the solution (north star)
+ITER_TOL = 2    # iterations to tolerance
+
+
+def oracle_solve(case, **kw):
+    from oracle import cpu
+    return cpu.solve(case["system"], kw.pop("x0", None), periodic=case["periodic"], **kw)
+
+
+def gpu_solve(case, conf, x0=None, maxnorm=False, flags=0):
+    shape = case["system"].shape[:3]
+    solver = SolverConjugateCuda(conf, {"residual_max": maxnorm},
+                                 Mesh(shape=shape, periodic=case["periodic"]), flags)
+    x = np.full(shape, np.nan)
+    info = solver.Solve(case["system"], x0, x)
+    hist = solver.History(info.iter)
+    solver.close()
+    return x, info, hist
+
+
+def compare_solutions(case, x, xo):
+    # singular (pure Neumann / periodic) systems fix the solution up to a constant:
+    # the iteration never changes the mean, so both start and stay on the same one
+    return rel_max_abs(x, xo)
+
+
+VARIANTS = [pytest.param(0, id="tma+graph"),
+            pytest.param(capi.APHCG_NO_TMA, id="plain+graph"),
+            pytest.param(capi.APHCG_NO_TMA | capi.APHCG_NO_GRAPH, id="plain+nograph"),
+            pytest.param(capi.APHCG_NO_GRAPH, id="tma+nograph")]
+
+
+@pytest.mark.parametrize("flags", VARIANTS)
+def test_tlinear_32_converged(gpu, flags):
+    """The reference's own unit test system (src/test/linear/main.cpp), its command
+    line: --tol 1e-5 --maxiter 1000 (src/test/linear/test:12-16)."""
+    case = case_tlinear(32)
+    conf = Conf(tol=1e-5, miniter=0, maxiter=1000)
+    x, info, hist = gpu_solve(case, conf, flags=flags)
+    xo, it_o, res_o, hist_o = oracle_solve(case, tol=conf.tol, miniter=0, maxiter=conf.maxiter)
+    assert abs(info.iter - it_o) <= ITER_TOL
+    assert info.residual < conf.tol
+    # the reference's own acceptance check: error vs the exact solution
+    d = remove_mean(x - case["exact"])
+    do = remove_mean(xo - case["exact"])
+    assert np.abs(d).max() < 2 * np.abs(do).max() + 1e-12
+    n = min(len(hist), len(hist_o), 50)
+    np.testing.assert_allclose(hist[:n], hist_o[:n], rtol=1e-9)
+
+
+@pytest.mark.parametrize("flags", VARIANTS[:2])
+@pytest.mark.parametrize("name", ["tlinear48", "const40", "density32", "density_perz", "flat"])
+def test_converged_parity(gpu, name, flags):
+    case = {
+        "tlinear48": lambda: case_tlinear(48),
+        "const40": lambda: case_periodic_const(40),
+        "density32": lambda: case_density(32, rho_in=0.1),
+        "density_perz": lambda: case_density(32, periodic=(False, False, True), rho_in=0.1),
+        "flat": lambda: case_tlinear(None, shape=(4, 36, 130)),
+    }[name]()
+    rhs_norm = np.sqrt((case["system"][..., 7] ** 2).sum() / (1.0 / max(case["system"].shape[:3])) ** 3)
+    conf = Conf(tol=1e-11 * rhs_norm, miniter=0, maxiter=5000)
+    x, info, hist = gpu_solve(case, conf, flags=flags)
+    xo, it_o, res_o, hist_o = oracle_solve(case, tol=conf.tol, miniter=0, maxiter=conf.maxiter)
+    assert it_o < conf.maxiter, "oracle did not converge: bad test case"
+    assert abs(info.iter - it_o) <= ITER_TOL, (info.iter, it_o)
+    assert compare_solutions(case, x, xo) <= X_TOL
+
+
+def test_fixed_iterations_history(gpu):
+    """tol=0, maxiter=100 (the reference's run_bench setting) -> exactly 101
+    iterations (src/linear/linear.ipp:110-113) and the same residual history."""
+    case = case_tlinear(64)
+    conf = Conf(tol=0.0, miniter=0, maxiter=100)
+    x, info, hist = gpu_solve(case, conf)
+    xo, it_o, res_o, hist_o = oracle_solve(case, tol=0.0, miniter=0, maxiter=100)
+    assert info.iter == it_o == 101
+    # known answer regenerated from the reference: res=4.199885e-01
+    assert abs(res_o - 4.199885e-01) < 1e-6
+    np.testing.assert_allclose(hist, hist_o, rtol=1e-7)
+    assert rel_max_abs(x, xo) < 1e-8
+
+
+def test_initial_guess_and_alias(gpu):
+    case = case_tlinear(32)
+    x0 = random_guess(case["system"].shape[:3])
+    conf = Conf(tol=1e-7, miniter=0, maxiter=2000)
+    xo, it_o, _, _ = oracle_solve(case, x0=x0, tol=conf.tol, miniter=0, maxiter=conf.maxiter)
+    shape = x0.shape
+    solver = SolverConjugateCuda(conf, {}, Mesh(shape=shape, periodic=case["periodic"]))
+    x = x0.copy()
+    info = solver.Solve(case["system"], x, x)  # fc_init == &fc_sol (linear.h:40)
+    assert abs(info.iter - it_o) <= ITER_TOL
+    assert rel_max_abs(x, xo) <= X_TOL
+    # SetConf between solves (hydro.ipp:2351-2353), zero guess
+    solver.SetConf(Conf(tol=1e-3, miniter=0, maxiter=2000))
+    x2 = np.zeros(shape)
+    info2 = solver.Solve(case["system"], None, x2)
+    xo2, it_o2, _, _ = oracle_solve(case, tol=1e-3, miniter=0, maxiter=2000)
+    assert abs(info2.iter - it_o2) <= ITER_TOL
+    assert rel_max_abs(x2, xo2) < 1e-9
+    solver.close()
+
+
+def test_miniter_maxiter_rules(gpu):
+    case = case_tlinear(16)
+    for conf in [Conf(tol=1e30, miniter=7, maxiter=100),   # converged at once, miniter wins
+                 Conf(tol=0.0, miniter=0, maxiter=5),      # maxiter+1 iterations
+                 Conf(tol=0.0, miniter=9, maxiter=3),      # miniter > maxiter
+                 Conf(tol=1e30, miniter=0, maxiter=0)]:    # one iteration at least
+        x, info, _ = gpu_solve(case, conf)
+        xo, it_o, res_o, _ = oracle_solve(case, tol=conf.tol, miniter=conf.miniter,
+                                          maxiter=conf.maxiter)
+        assert info.iter == it_o, (conf, info.iter, it_o)
+        assert rel_max_abs(x, xo) < 1e-10
+        assert abs(info.residual - res_o) <= 1e-9 * abs(res_o)
+
+
+def test_maxnorm(gpu):
+    case = case_tlinear(32)
+    conf = Conf(tol=1e-2, miniter=0, maxiter=1000)
+    x, info, hist = gpu_solve(case, conf, maxnorm=True)
+    xo, it_o, res_o, hist_o = oracle_solve(case, tol=conf.tol, miniter=0, maxiter=1000, maxnorm=True)
+    assert abs(info.iter - it_o) <= ITER_TOL
+    n = min(len(hist), len(hist_o), 30)
+    np.testing.assert_allclose(hist[:n], hist_o[:n], rtol=1e-8)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 2), (3, 5, 7), (5, 9, 130), (2, 8, 128), (9, 16, 258),
+                                   (33, 8, 64), (1, 40, 40)])
+def test_ragged_shapes(gpu, shape):
+    """odd nx (scalar path), partial tiles, single plane (2-D), tiny meshes"""
+    s, exact = __import__("aphros_b200").systems.tlinear_system(None, shape=shape)
+    case = dict(system=s, periodic=(True, True, True))
+    conf = Conf(tol=0.0, miniter=0, maxiter=12)
+    x, info, hist = gpu_solve(case, conf)
+    xo, it_o, res_o, hist_o = oracle_solve(case, tol=0.0, miniter=0, maxiter=12)
+    assert info.iter == it_o
+    k = int(np.argmax(hist_o < 1e-9 * hist_o[0])) if (hist_o < 1e-9 * hist_o[0]).any() else len(hist_o)
+    k = max(k, 1)
+    np.testing.assert_allclose(hist[:k], hist_o[:k], rtol=1e-7)
+
+
+def test_apply_operator(gpu):
+    """stage "iter" operator alone (linear.ipp:65-72): differences only from FMA"""
+    from oracle import cpu
+    for case in [case_tlinear(24), case_density(24, periodic=(False, True, False)),
+                 case_tlinear(None, shape=(5, 9, 130))]:
+        shape = case["system"].shape[:3]
+        v = random_guess(shape, seed=11)
+        solver = SolverConjugateCuda(Conf(), {}, Mesh(shape=shape, periodic=case["periodic"]))
+        solver.UploadSystem(case["system"])
+        out = solver.Apply(v)
+        ref = cpu.apply(case["system"], v, periodic=case["periodic"])
+        scale = cpu.apply(np.abs(case["system"]), np.abs(v), periodic=case["periodic"])
+        assert (np.abs(out - ref) <= 8 * np.finfo(float).eps * scale + 1e-300).all()
+        solver.close()
+
+
+def test_strided_fields(gpu):
+    """fields laid out like the reference's FieldCell with hl=2 halos and one padding
+    cell per direction (src/geom/mesh.ipp:60-113)"""
+    case = case_tlinear(16)
+    n, hl = 16, 2
+    full = n + 2 * hl + 1
+    sys_full = np.full((full, full, full, 8), np.nan)
+    sys_full[hl:hl + n, hl:hl + n, hl:hl + n] = case["system"]
+    x_full = np.full((full, full, full), 777.0)
+    conf = Conf(tol=1e-8, miniter=0, maxiter=1000)
+    solver = SolverConjugateCuda(conf, {}, Mesh(shape=(n, n, n), periodic=case["periodic"]))
+    xv = x_full[hl:hl + n, hl:hl + n, hl:hl + n]
+    xv[...] = 0
+    info = solver.Solve(sys_full[hl:hl + n, hl:hl + n, hl:hl + n], xv, xv)
+    solver.close()
+    xo, it_o, _, _ = oracle_solve(case, tol=conf.tol, miniter=0, maxiter=1000)
+    assert abs(info.iter - it_o) <= ITER_TOL
+    assert rel_max_abs(xv, xo) <= X_TOL
+    mask = np.ones_like(x_full, dtype=bool)
+    mask[hl:hl + n, hl:hl + n, hl:hl + n] = False
+    assert (x_full[mask] == 777.0).all(), "cells outside the inner block were touched"
+
+
+def test_deterministic(gpu):
+    case = case_density(32, rho_in=0.01)
+    conf = Conf(tol=0.0, miniter=0, maxiter=60)
+    x1, i1, h1 = gpu_solve(case, conf)
+    x2, i2, h2 = gpu_solve(case, conf)
+    assert np.array_equal(x1, x2) and np.array_equal(h1, h2)
+
+
+def test_jacobi(gpu):
+    """SolverJacobi twin (linear.ipp:152-237); known answer of the reference test:
+    32^3, tol 1e-5 -> iter=613 res=9.981133e-06"""
+    from oracle import cpu
+    case = case_tlinear(32)
+    conf = Conf(tol=1e-5, miniter=0, maxiter=1000)
+    solver = SolverJacobiCuda(conf, {}, Mesh(shape=(32, 32, 32), periodic=case["periodic"]))
+    x = np.zeros((32, 32, 32))
+    info = solver.Solve(case["system"], None, x)
+    solver.close()
+    xo, it_o, res_o, _ = cpu.solve(case["system"], tol=1e-5, miniter=0, maxiter=1000, method="jacobi")
+    assert it_o == 613 and abs(res_o - 9.981133e-06) < 1e-11
+    assert abs(info.iter - it_o) <= ITER_TOL
+    assert rel_max_abs(x, xo) < 1e-9
+
+
+def test_device_assembly_matches_host_generator(gpu):
+    sys.modules  # noqa
+    from aphros_b200 import systems
+    n = 48
+    sph = systems.random_spheres(16, 5)
+    ref, _ = systems.density_poisson_system(n, nspheres=16, seed=5)
+    solver = SolverConjugateCuda(Conf(), {}, Mesh(shape=(n, n, n), periodic=(False, False, False)))
+    solver.AssembleSpheres(sph)
+    got = solver.DownloadSystem()
+    solver.close()
+    assert np.array_equal(got[..., :7], ref[..., :7])
+    scale = np.abs(ref[..., 7]).max()
+    assert np.abs(got[..., 7] - ref[..., 7]).max() <= 1e-14 * scale + 1e-22
+
+
+import sys  # noqa: E402
