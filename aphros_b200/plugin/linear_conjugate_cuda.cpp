@@ -1,0 +1,214 @@
+// aphros-side adapter: registers libaphcg.so as the linear-solver modules
+//   "conjugate_cuda"  (sibling of "conjugate",  src/linear/linear.ipp:239-253)
+//   "jacobi_cuda"     (sibling of "jacobi",     src/linear/linear.ipp:255-265)
+// behind the reference's own factory, so that `set string linsolver_symm
+// conjugate_cuda` selects it with no change to aphros
+// (ULinear<M>::MakeLinearSolver, src/util/linear.ipp:10-28).
+//
+// Compiled against the reference headers (-I/root/reference/src); loaded with
+// LD_PRELOAD / dlopen / or linked in: the static registrar below adds the
+// modules to ModuleLinear<M>'s table (src/util/module.h:21-43) at load time.
+// All arithmetic happens in libaphcg.so through the C ABI (include/aphcg.h).
+//
+// Calling convention: Solve is a stage coroutine entered once
+// per block per stage.  Blocks of one rank copy their inner cells into
+// rank-wide pinned arrays owned by the lead block (the reference's precedent is
+// LocalToShared/SharedToLocal, src/opencl/opencl.h:30-64); the lead block alone
+// talks to the GPU, inside ONE stage; every block then copies its part of the
+// solution back and requests the usual halo exchange of fc_sol
+// (src/linear/linear.ipp:116-118).  Unlike conjugate_cl it needs no shared-mesh
+// Comm, so it works under the native, local and cubismnc backends alike.
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <string>
+
+#include "linear/linear.h"
+
+#include "aphcg.h"
+
+namespace linear {
+
+template <class M>
+class SolverCuda : public Solver<M> {
+ public:
+  using Base = Solver<M>;
+  using Conf = typename Base::Conf;
+  using Info = typename Base::Info;
+  using Scal = typename M::Scal;
+  using Expr = typename M::Expr;
+  using MIdx = typename M::MIdx;
+  enum class Method { conjugate, jacobi };
+
+  SolverCuda(const Conf& conf, Method method, bool maxnorm, int device, unsigned flags,
+             const M& m)
+      : Base(conf), method_(method) {
+    static_assert(M::dim == 3, "conjugate_cuda: 3-D meshes only");
+    static_assert(sizeof(Expr) == 8 * sizeof(double), "row must be 8 doubles");
+    if (m.IsLead()) {
+      // one device object per rank, owned by the lead block
+      // (cf. src/linear/conjugate_cl.ipp:29-35)
+      shared_obj_ = std::make_unique<Shared>();
+      auto& s = *shared_obj_;
+      const auto& ms = m.GetShared();
+      const MIdx size = ms.GetInBlockCells().GetSize();
+      s.origin = ms.GetInBlockCells().GetBegin();
+      s.size = size;
+      aphcg_desc d;
+      std::memset(&d, 0, sizeof(d));
+      d.nx = size[0];
+      d.ny = size[1];
+      d.nz = size[2];
+      fassert(
+          ms.GetGlobalSize() == size,
+          "conjugate_cuda: one rank must own the whole domain (run aphros with "
+          "px=py=pz=1; the multi-GPU slab path is driven through the C ABI)");
+      for (int i = 0; i < 3; ++i) d.periodic[i] = m.flags.is_periodic[i] ? 1 : 0;
+      d.cell_volume = m.GetCellSize().prod();
+      d.device = device;
+      d.rank = 0;
+      d.nranks = 1;
+      d.z0 = 0;
+      d.nz_local = size[2];
+      d.flags = flags | (maxnorm ? APHCG_MAXNORM : 0);
+      Check(aphcg_create(&s.handle, &d));
+      const uint64_t n = uint64_t(size[0]) * size[1] * size[2];
+      Check(aphcg_host_alloc(reinterpret_cast<void**>(&s.rows), n * 8 * sizeof(double)));
+      Check(aphcg_host_alloc(reinterpret_cast<void**>(&s.x), n * sizeof(double)));
+      shared_ = &s;
+    }
+  }
+  ~SolverCuda() override {
+    if (shared_obj_) {
+      auto& s = *shared_obj_;
+      if (s.rows) aphcg_host_free(s.rows);
+      if (s.x) aphcg_host_free(s.x);
+      if (s.handle) aphcg_destroy(s.handle);
+    }
+  }
+
+  Info Solve(
+      const FieldCell<Expr>& fc_system, const FieldCell<Scal>* fc_init,
+      FieldCell<Scal>& fc_sol, M& m) override {
+    auto sem = m.GetSem(__func__);
+    struct {
+      Info info;
+    } * ctx(sem);
+    auto& t = *ctx;
+    if (sem("bcast")) {
+      m.BcastFromLead(&shared_);
+    }
+    if (sem("gather")) {
+      auto& s = *shared_;
+      // rows and guess of this block -> rank-wide pinned arrays (disjoint ranges,
+      // safe when blocks run concurrently under OpenMP, src/distr/distr.ipp:90-97)
+      for (auto c : m.Cells()) {
+        const size_t i = s.Index(m.GetIndexCells().GetMIdx(c));
+        std::memcpy(s.rows + 8 * i, &fc_system[c][0], 8 * sizeof(double));
+        s.x[i] = fc_init ? (*fc_init)[c] : Scal(0);
+      }
+    }
+    if (sem("solve") && m.IsLead()) {
+      auto& s = *shared_;
+      aphcg_conf conf;
+      conf.tol = this->conf.tol;
+      conf.miniter = this->conf.miniter;
+      conf.maxiter = this->conf.maxiter;
+      aphcg_info info;
+      if (method_ == Method::conjugate) {
+        // x doubles as guess and solution (fc_init may alias fc_sol, linear.h:40)
+        Check(aphcg_solve(
+            s.handle, s.rows, nullptr, fc_init ? s.x : nullptr, nullptr, s.x, nullptr, &conf,
+            &info));
+      } else {
+        Check(aphcg_upload_system(s.handle, s.rows, nullptr));
+        Check(aphcg_upload_guess(s.handle, fc_init ? s.x : nullptr, nullptr));
+        Check(aphcg_run_jacobi(s.handle, &conf, &info));
+        Check(aphcg_download_solution(s.handle, s.x, nullptr));
+      }
+      s.info.residual = info.residual;
+      s.info.iter = info.iter;
+    }
+    if (sem("scatter")) {
+      auto& s = *shared_;
+      if (!fc_sol.size()) {
+        fc_sol.Reinit(m);  // callers may pass an empty field (cf. opencl.h:36-40)
+      }
+      for (auto c : m.Cells()) {
+        fc_sol[c] = s.x[s.Index(m.GetIndexCells().GetMIdx(c))];
+      }
+      t.info = s.info;
+      m.Comm(&fc_sol, M::CommStencil::direct_one);
+      if (m.flags.linreport && m.IsRoot()) {
+        std::cerr << std::scientific;
+        std::cerr << std::string("linear(") +
+                         (method_ == Method::conjugate ? "conjugate_cuda" : "jacobi_cuda") +
+                         ") '" + fc_system.GetName() + "':"
+                  << " res=" << t.info.residual << " iter=" << t.info.iter << std::endl;
+      }
+    }
+    if (sem()) {
+      // the Comm of fc_sol completes before the context is destroyed (linear.ipp:126-127)
+    }
+    return t.info;
+  }
+
+ private:
+  struct Shared {
+    aphcg_t* handle = nullptr;
+    double* rows = nullptr;  // pinned, rank-wide, [nz][ny][nx][8]
+    double* x = nullptr;     // pinned, rank-wide, guess in / solution out
+    MIdx origin;
+    MIdx size;
+    Info info;
+    size_t Index(MIdx w) const {
+      const MIdx l = w - origin;
+      return (size_t(l[2]) * size[1] + l[1]) * size[0] + l[0];
+    }
+  };
+  // CUDA / NCCL failures surface like any other aphros error
+  // (fassert -> aphros_SetError + throw, src/util/logger.h:44-60)
+  static void Check(int rc) {
+    fassert(rc == 0, std::string("conjugate_cuda: ") + aphcg_last_error());
+  }
+
+  Method method_;
+  std::unique_ptr<Shared> shared_obj_;
+  Shared* shared_ = nullptr;
+};
+
+template <class M>
+class ModuleLinearConjugateCuda : public ModuleLinear<M> {
+ public:
+  ModuleLinearConjugateCuda() : ModuleLinear<M>("conjugate_cuda") {}
+  std::unique_ptr<Solver<M>> Make(const Vars& var, std::string prefix, const M& m) override {
+    auto key = [prefix](std::string name) { return "linsolver_" + prefix + "_" + name; };
+    // new keys are read with defaults: Vars::operator[] throws when a key is missing
+    const bool maxnorm = var.Int(key("maxnorm"), 0);
+    unsigned flags = 0;
+    if (!var.Int(key("cuda_graph"), 1)) flags |= APHCG_NO_GRAPH;
+    if (!var.Int(key("cuda_tma"), 1)) flags |= APHCG_NO_TMA;
+    return std::make_unique<SolverCuda<M>>(
+        this->GetConf(var, prefix), SolverCuda<M>::Method::conjugate, maxnorm,
+        var.Int("cuda_device", 0), flags, m);
+  }
+};
+
+template <class M>
+class ModuleLinearJacobiCuda : public ModuleLinear<M> {
+ public:
+  ModuleLinearJacobiCuda() : ModuleLinear<M>("jacobi_cuda") {}
+  std::unique_ptr<Solver<M>> Make(const Vars& var, std::string prefix, const M& m) override {
+    return std::make_unique<SolverCuda<M>>(
+        this->GetConf(var, prefix), SolverCuda<M>::Method::jacobi, false,
+        var.Int("cuda_device", 0), 0u, m);
+  }
+};
+
+using M3 = MeshCartesian<double, 3>;
+bool kReg_conjugate_cuda[] = {
+    RegisterModule<ModuleLinearConjugateCuda<M3>>(),
+    RegisterModule<ModuleLinearJacobiCuda<M3>>(),
+};
+
+} // namespace linear

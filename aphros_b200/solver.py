@@ -60,7 +60,8 @@ class Mesh:
 
     def __post_init__(self):
         if self.cell_volume is None:
-            self.cell_volume = (1.0 / max(self.shape)) ** 3
+            from .systems import cell_volume
+            self.cell_volume = cell_volume(self.shape)
         if self.nz_local is None:
             self.nz_local = self.shape[0]
 

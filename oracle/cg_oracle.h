@@ -40,7 +40,7 @@ typedef struct {
 /* sys: nx*ny*nz rows of 8 doubles [c,x-,x+,y-,y+,z-,z+,const]
  *      (src/geom/mesh.h:484-485, src/linear/linear.h:34-44).
  * x0 : initial guess or NULL (zero guess, linear.ipp:43-47).
- * x  : out, solution. history: NULL or maxiter+2 doubles, residual after each
+ * x  : out, solution. history: NULL or max(maxiter,miniter)+2 doubles, residual after each
  *      completed iteration.  Returns 0, or -1 on allocation failure. */
 int cg_oracle_conjugate(
     const cg_oracle_desc* d, const double* sys, const double* x0, double* x,

@@ -73,16 +73,31 @@ def _desc(shape, periodic, block, cell_volume, tol, miniter, maxiter, maxnorm):
     return d
 
 
+def reference_cell_volume(shape, block=None):
+    """m.GetCellSize().prod() as the reference's ROOT block computes it: the block
+    spans [0, bs*h] with h = extent/max(n) (src/kernel/kernelmesh.h:29-44) and
+    cell_size = span/bs per direction (src/geom/mesh.ipp:84-86), which is h only
+    up to rounding; prod() multiplies x, y, z in order."""
+    nz, ny, nx = shape
+    b = block if block is not None else (nx, ny, nz)
+    if isinstance(b, int):
+        b = (b, b, b)
+    b = [bb if bb > 0 else n for bb, n in zip(b, (nx, ny, nz))]
+    h = 1.0 / max(shape)
+    cs = [(float(bb) * h - 0.0 * h) / float(bb) for bb in b]
+    return cs[0] * cs[1] * cs[2]
+
+
 def solve(system, x0=None, *, periodic=(True, True, True), cell_volume=None, tol=0.0,
           miniter=0, maxiter=100, maxnorm=False, block=None, method="conjugate"):
     """Run the C restatement.  system: (nz,ny,nx,8).  Returns (x, iter, residual, history)."""
     system = np.ascontiguousarray(system, dtype=np.float64)
     shape = system.shape[:3]
     if cell_volume is None:
-        cell_volume = (1.0 / max(shape)) ** 3
+        cell_volume = reference_cell_volume(shape, block)
     x0c = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
     x = np.empty(shape, dtype=np.float64)
-    hist = np.zeros(maxiter + 2, dtype=np.float64)
+    hist = np.zeros(max(maxiter, miniter) + 2, dtype=np.float64)
     res = ctypes.c_double()
     it = ctypes.c_int()
     d = _desc(shape, periodic, block, cell_volume, tol, miniter, maxiter, maxnorm)

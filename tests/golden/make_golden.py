@@ -1,0 +1,80 @@
+"""Generates tests/golden/*.npz from the REFERENCE ITSELF (oracle/_ref/ref_cg =
+linear::SolverConjugate / SolverJacobi compiled from /root/reference/src by
+oracle/ref/Makefile).  Run in the build container (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Each fixture stores the inputs' recipe (regenerated from seeds by
+aphros_b200.systems, checked by a checksum), the reference's iteration count,
+final residual and solution.  Small on purpose (<= 24^3).
+"""
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from aphros_b200 import systems  # noqa: E402
+from oracle import cpu  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build_case(name):
+    """name -> (system, x0, periodic, kwargs for the solver)"""
+    rng = np.random.default_rng(12345)
+    if name == "tlinear16_b8":
+        s, _ = systems.tlinear_system(16)
+        return s, None, (True, True, True), dict(tol=1e-5, maxiter=1000, block=8)
+    if name == "tlinear24_b12_guess":
+        s, _ = systems.tlinear_system(24)
+        return s, rng.standard_normal((24, 24, 24)), (True, True, True), dict(
+            tol=1e-7, maxiter=1000, block=12)
+    if name == "tlinear_ragged":
+        s, _ = systems.tlinear_system(None, shape=(6, 10, 20))
+        return s, None, (True, True, True), dict(tol=0.0, maxiter=30, block=(10, 5, 3))
+    if name == "density24_neumann":
+        s, _ = systems.density_poisson_system(24, nspheres=6, seed=3, rho_in=1e-2)
+        tol = 1e-9 * float(np.sqrt((s[..., 7] ** 2).sum() / systems.cell_volume((24, 24, 24))))
+        return s, None, (False, False, False), dict(tol=tol, maxiter=3000, block=8)
+    if name == "density16_1000to1_fixed":
+        s, _ = systems.density_poisson_system(16, nspheres=4, seed=9, rho_in=1e-3)
+        return s, None, (False, False, False), dict(tol=0.0, maxiter=100, block=16)
+    if name == "const20_periodic_maxnorm":
+        s, _ = systems.periodic_constant_system(20)
+        return s, None, (True, True, True), dict(tol=1e-4, maxiter=500, block=10, maxnorm=True)
+    if name == "tlinear16_miniter":
+        s, _ = systems.tlinear_system(16)
+        return s, None, (True, True, True), dict(tol=1e30, maxiter=100, miniter=13, block=16)
+    if name == "tlinear16_jacobi":
+        s, _ = systems.tlinear_system(16)
+        return s, None, (True, True, True), dict(tol=1e-4, maxiter=2000, block=8, solver="jacobi")
+    raise KeyError(name)
+
+
+CASES = ["tlinear16_b8", "tlinear24_b12_guess", "tlinear_ragged", "density24_neumann",
+         "density16_1000to1_fixed", "const20_periodic_maxnorm", "tlinear16_miniter",
+         "tlinear16_jacobi"]
+
+
+def checksum(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    assert cpu.have_reference(), "build oracle/_ref first: make -C oracle/ref"
+    for name in CASES:
+        s, x0, per, kw = build_case(name)
+        x, it, res, _ = cpu.solve_reference(s, x0, periodic=per, **kw)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x, iter=it, residual=res,
+                            system_sha256=checksum(s))
+        print(name, it, res)
+
+
+if __name__ == "__main__":
+    main()
