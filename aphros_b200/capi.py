@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libaphcg.so")
 APHCG_MAXNORM = 1 << 0
 APHCG_NO_GRAPH = 1 << 1
 APHCG_NO_TMA = 1 << 2
+APHCG_NO_SYM = 1 << 3
 UNIQUE_ID_BYTES = 128
 IPC_BYTES = 128
 

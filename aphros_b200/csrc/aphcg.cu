@@ -91,10 +91,14 @@ struct aphcg {
   DevPtrs d{};
   bool have_system = false, have_guess = false;
   // loop graph
-  cudaGraphExec_t gexec = nullptr;
+  cudaGraphExec_t gexec = nullptr;      // general-storage loop
+  cudaGraphExec_t gexec_sym = nullptr;  // symmetric-storage loop
   cudaGraphExec_t gexec_jacobi = nullptr;
   bool use_graph = true;
   bool use_tma = false;
+  bool sym = false;       // resident matrix verified symmetric -> 4-stream kernel
+  bool allow_sym = true;
+  int* d_flag = nullptr;
   TmaPlan* tma = nullptr;
   // comm
   ncclComm_t comm = nullptr;
@@ -115,6 +119,8 @@ int SetDevice(aphcg_t* h) {
 
 void InvalidateGraphs(aphcg_t* h) {
   if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  if (h->gexec_sym) cudaGraphExecDestroy(h->gexec_sym);
+  h->gexec_sym = nullptr;
   if (h->gexec_jacobi) cudaGraphExecDestroy(h->gexec_jacobi);
   h->gexec = nullptr;
   h->gexec_jacobi = nullptr;
@@ -166,7 +172,7 @@ int AllReduce(aphcg_t* h, double* p, ncclRedOp_t op) {
 // One CG iteration enqueued on h->stream.
 int EnqueueIteration(aphcg_t* h) {
   if (h->use_tma) {
-    launch_dir_spmv_tma(h->tma, h->g, h->d, h->single, h->stream);
+    launch_dir_spmv_tma(h->tma, h->g, h->d, h->single, h->sym, h->stream);
   } else {
     launch_dir_spmv_plain(h->g, h->d, h->vx, h->single, h->stream);
   }
@@ -270,6 +276,23 @@ int CopyPlanes(const aphcg_t* h, void* dst, const void* src, const aphcg_layout&
   return 0;
 }
 
+// The system just became resident: decide whether the 4-stream (symmetric
+// storage) kernel may be used for it.  One pass over the off-diagonals.
+int SystemResident(aphcg_t* h) {
+  h->have_system = true;
+  h->sym = false;
+  if (!h->use_tma || !h->allow_sym) return 0;
+  int flag = 0;
+  CK(cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream));
+  launch_check_symmetry(h->g, h->d, h->d_flag, h->stream);
+  h->launches++;
+  CK(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  h->sym = (flag == 0);
+  return 0;
+}
+
 int EnsureStage(aphcg_t* h) {
   for (int b = 0; b < 2; ++b) {
     if (!h->stage[b]) {
@@ -309,7 +332,7 @@ int EnsureHistory(aphcg_t* h, int maxiter) {
 
 // Replays iterations until the device-side exit rule fires.
 int RunLoop(aphcg_t* h, bool jacobi, const aphcg_conf* conf) {
-  cudaGraphExec_t* gx = jacobi ? &h->gexec_jacobi : &h->gexec;
+  cudaGraphExec_t* gx = jacobi ? &h->gexec_jacobi : (h->sym ? &h->gexec_sym : &h->gexec);
   if (h->use_graph && !*gx) {
     if (int rc = BuildGraph(h, jacobi, gx)) return rc;
   }
@@ -429,6 +452,7 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
   CKC(cudaMalloc(&h->ap, nb));
   CKC(cudaMalloc(&h->slab, sizeof(double) * 3 * (size_t)g.ptotal));
   CKC(cudaMemset(h->slab, 0, sizeof(double) * 3 * (size_t)g.ptotal));
+  CKC(cudaMalloc(&h->d_flag, sizeof(int)));
   CKC(cudaMalloc(&h->st, sizeof(CgState)));
   CKC(cudaMemset(h->st, 0, sizeof(CgState)));
   CKC(cudaHostAlloc(&h->h_st, sizeof(CgState), cudaHostAllocDefault));
@@ -436,6 +460,8 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
   FillDevPtrs(h);
   SelfConnect(h);
   // TMA-staged kernel unless disabled or the geometry does not qualify
+  h->allow_sym = !(ds.flags & APHCG_NO_SYM);
+  if (const char* es = getenv("APHCG_SYM")) h->allow_sym = atoi(es) != 0;
   const char* env = getenv("APHCG_SPMV");
   bool want_tma = !(ds.flags & APHCG_NO_TMA);
   if (env && !strcmp(env, "plain")) want_tma = false;
@@ -477,6 +503,7 @@ int aphcg_destroy(aphcg_t* h) {
   cudaFree(h->ap);
   cudaFree(h->slab);
   cudaFree(h->st);
+  cudaFree(h->d_flag);
   cudaFree(h->history);
   cudaFree(h->partials);
   cudaFree(h->partials2);
@@ -521,8 +548,7 @@ int aphcg_upload_system(aphcg_t* h, const double* system, const aphcg_layout* la
     CK(cudaEventRecord(h->stage_free[b], h->stream));
   }
   CK(cudaGetLastError());
-  h->have_system = true;
-  return 0;
+  return SystemResident(h);
 }
 
 int aphcg_set_system_device(aphcg_t* h, const double* d_system, const aphcg_layout* layout) {
@@ -534,8 +560,7 @@ int aphcg_set_system_device(aphcg_t* h, const double* d_system, const aphcg_layo
                      h->rhs, h->stream);
   h->launches++;
   CK(cudaGetLastError());
-  h->have_system = true;
-  return 0;
+  return SystemResident(h);
 }
 
 static int ScatterGuess(aphcg_t* h, const double* d_src, const aphcg_layout& l) {
@@ -739,9 +764,8 @@ int aphcg_assemble_spheres(aphcg_t* h, const double* spheres, int32_t nspheres, 
   if (d_sph) cudaFree(d_sph);
   if (e != cudaSuccess) return Fail(APHCG_ERR_CUDA, "assemble failed: %s", cudaGetErrorString(e));
   CK(cudaGetLastError());
-  h->have_system = true;
   h->have_guess = false;
-  return 0;
+  return SystemResident(h);
 }
 
 int aphcg_download_system(aphcg_t* h, double* system, const aphcg_layout* layout) {
@@ -893,7 +917,7 @@ int aphcg_profile_kernels(aphcg_t* h, int32_t iters, double* ms_dir_spmv, double
   for (int i = 0; i < iters; ++i) {
     CK(cudaEventRecord(ev[3 * i], h->stream));
     if (h->use_tma) {
-      launch_dir_spmv_tma(h->tma, h->g, h->d, true, h->stream);
+      launch_dir_spmv_tma(h->tma, h->g, h->d, true, h->sym, h->stream);
     } else {
       launch_dir_spmv_plain(h->g, h->d, h->vx, true, h->stream);
     }

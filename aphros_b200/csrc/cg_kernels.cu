@@ -158,50 +158,95 @@ __global__ void __launch_bounds__(kBX* kBY)
 
 // ------------------------------------------------------------------------------
 // k_update: r -= alpha*Ap, sum r^2, max|r|, ghost copies of r ("iter2"+"check").
+// Pure streaming (24 B/cell): a CTA owns kUR consecutive rows of one plane range,
+// every thread keeps kUR independent 128-bit load pairs in flight.
 // ------------------------------------------------------------------------------
+constexpr int kUT = 256;  // threads
+constexpr int kUR = 4;    // rows per thread (loads in flight)
+constexpr int kUZ = 4;    // planes per CTA
+
 template <int VX, bool kSingle>
-__global__ void __launch_bounds__(kBX* kBY) k_update(const Geom g, const DevPtrs d) {
+__global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
   __shared__ double sm[32];
   __shared__ int sm_flag;
   CgState* st = d.st;
   if (st->done) return;
   const double alpha = cg_alpha(st);
   double* __restrict__ r = d.r;
-  const Tile t = my_tile<VX>(g);
+  // x-chunks of kUT*VX cells; blockIdx.x enumerates (x-chunk, row-group)
+  const int xchunks = (g.nx + kUT * VX - 1) / (kUT * VX);
+  const int xc = blockIdx.x % xchunks;
+  const int j0 = (blockIdx.x / xchunks) * kUR;
+  const int i = (xc * kUT + threadIdx.x) * VX;
+  const int k0 = blockIdx.y * kUZ;
+  const int k1 = min(k0 + kUZ, g.nzl);
   double acc = 0.0, amax = 0.0;
-  if (t.active) {
-    for (int k = t.k0; k < t.k1; ++k) {
-      const int64_t idc = t.i + t.j * g.cy + k * g.cz;
-      const int64_t idp = g.poff + t.i + t.j * g.py + k * g.pz;
-      const Vec<VX> ap = ldv_stream<VX>(d.ap + idc);
-      Vec<VX> rv = ldv<VX>(r + idp);
+  if (i < g.nx) {
+    for (int k = k0; k < k1; ++k) {
+      Vec<VX> ap[kUR], rv[kUR];
 #pragma unroll
-      for (int v = 0; v < VX; ++v) {
-        rv.v[v] = fma(-alpha, ap.v[v], rv.v[v]);  // linear.ipp:89
-        acc = fma(rv.v[v], rv.v[v], acc);         // :90
-        amax = fmax(amax, fabs(rv.v[v]));         // :91
+      for (int u = 0; u < kUR; ++u) {
+        const int j = j0 + u;
+        if (j < g.ny) {
+          ap[u] = ldv_stream<VX>(d.ap + i + j * g.cy + k * g.cz);
+          rv[u] = ldv_stream<VX>(r + g.poff + i + j * g.py + k * g.pz);
+        }
       }
-      stv<VX>(r + idp, rv);
-      store_images<VX>(g, r, idp, t.i, t.j, k, rv, d.r_lo_dst, d.r_hi_dst);
+#pragma unroll
+      for (int u = 0; u < kUR; ++u) {
+        const int j = j0 + u;
+        if (j < g.ny) {
+          const int64_t idp = g.poff + i + j * g.py + k * g.pz;
+#pragma unroll
+          for (int v = 0; v < VX; ++v) {
+            rv[u].v[v] = fma(-alpha, ap[u].v[v], rv[u].v[v]);  // linear.ipp:89
+            acc = fma(rv[u].v[v], rv[u].v[v], acc);            // :90
+            amax = fmax(amax, fabs(rv[u].v[v]));               // :91
+          }
+          stv<VX>(r + idp, rv[u]);
+          store_images<VX>(g, r, idp, i, j, k, rv[u], d.r_lo_dst, d.r_hi_dst);
+        }
+      }
     }
   }
   if (d.r_lo_dst != nullptr || d.r_hi_dst != nullptr) __threadfence_system();
   const double bsum = block_reduce<false>(acc, sm);
   const double bmax = block_reduce<true>(amax, sm);
-  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  const int tid = threadIdx.x;
+  const unsigned nblk = gridDim.x * gridDim.y, bid = blockIdx.x + gridDim.x * blockIdx.y;
   if (tid == 0) {
-    d.partials[block_id()] = bsum;
-    d.partials2[block_id()] = bmax;
+    d.partials[bid] = bsum;
+    d.partials2[bid] = bmax;
   }
-  if (last_block(&st->counter_b, num_blocks(), &sm_flag)) {
-    const double tot = reduce_slots<false>(d.partials, num_blocks(), sm);
-    const double mx = reduce_slots<true>(d.partials2, num_blocks(), sm);
+  if (last_block(&st->counter_b, nblk, &sm_flag)) {
+    const double tot = reduce_slots<false>(d.partials, nblk, sm);
+    const double mx = reduce_slots<true>(d.partials2, nblk, sm);
     if (tid == 0) {
       st->loc_sum = tot;
       st->loc_max = mx;
       if (kSingle) cg_finish_upd(st, d.history, tot, mx);
     }
   }
+}
+
+static dim3 update_grid(const Geom& g, int vx) {
+  const int xchunks = (g.nx + kUT * vx - 1) / (kUT * vx);
+  return dim3(xchunks * ((g.ny + kUR - 1) / kUR), (g.nzl + kUZ - 1) / kUZ);
+}
+
+// symmetry check of the off-diagonals inside the slab (see cg_launch.h)
+__global__ void k_check_symmetry(const Geom g, const DevPtrs d, int* flag) {
+  bool bad = false;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < g.ncell;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(c % g.nx);
+    const int j = (int)((c / g.nx) % g.ny);
+    const int k = (int)(c / g.cz);
+    if (i + 1 < g.nx) bad |= !(d.a[2][c] == d.a[1][c + 1]);
+    if (j + 1 < g.ny) bad |= !(d.a[4][c] == d.a[3][c + g.cy]);
+    if (k + 1 < g.nzl) bad |= !(d.a[6][c] == d.a[5][c + g.cz]);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
 // Multi-GPU: runs after the all-reduce of loc_sum / loc_max.
@@ -462,8 +507,9 @@ static dim3 tile_grid(const Geom& g, int vx) {
 }
 
 unsigned tile_blocks(const Geom& g, int vx) {
-  const dim3 gr = tile_grid(g, vx);
-  return gr.x * gr.y * gr.z;
+  const dim3 gr = tile_grid(g, vx), gu = update_grid(g, vx);
+  const unsigned a = gr.x * gr.y * gr.z, b = gu.x * gu.y * gu.z;
+  return a > b ? a : b;
 }
 
 #define APHCG_DISPATCH_VX(vx, ...) \
@@ -487,8 +533,12 @@ void launch_dir_spmv_plain(const Geom& g, const DevPtrs& d, int vx, bool single,
   });
 }
 
+void launch_check_symmetry(const Geom& g, const DevPtrs& d, int* flag, cudaStream_t s) {
+  k_check_symmetry<<<148 * 8, 256, 0, s>>>(g, d, flag);
+}
+
 void launch_update(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s) {
-  const dim3 gr = tile_grid(g, vx), bl(kBX, kBY);
+  const dim3 gr = update_grid(g, vx), bl(kUT);
   APHCG_DISPATCH_VX(vx, {
     if (single)
       k_update<VX, true><<<gr, bl, 0, s>>>(g, d);

@@ -36,8 +36,12 @@ struct TmaPlan;  // opaque: tensor maps + launch geometry
 TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen);
 void tma_plan_destroy(TmaPlan* p);
 unsigned tma_plan_blocks(const TmaPlan* p);
-void launch_dir_spmv_tma(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool single,
+// sym: read 4 coefficient streams instead of 7 (matrix verified symmetric)
+void launch_dir_spmv_tma(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool single, bool sym,
                          cudaStream_t s);
+// sets *flag (device int) to 1 if any off-diagonal pair differs: a2[c] != a1[c+1],
+// a4[c] != a3[c+row], a6[c] != a5[c+plane] (inside this slab)
+void launch_check_symmetry(const Geom& g, const DevPtrs& d, int* flag, cudaStream_t s);
 
 // device-side synthetic assembly (cg_assemble.cu)
 void launch_assemble_spheres(const Geom& g, const DevPtrs& d, double* const* a, double* rhs,

@@ -26,17 +26,27 @@ namespace acg {
 
 namespace {
 
-constexpr int TX = 128;      // tile cells along x
-constexpr int TY = 8;        // tile rows
-constexpr int NT = 256;      // threads per CTA
-constexpr int BW = TX + 4;   // box width: x0-2 .. x0+TX+1 (keeps inner pairs 16-byte aligned)
-constexpr int BH = TY + 2;   // box height: y0-1 .. y0+TY
-constexpr int BOX = BW * BH;              // doubles per box
-constexpr int BOXB = (BOX * 8 + 127) / 128 * 128;  // bytes, 128-aligned for TMA
-constexpr int S = 3;         // TMA stages in flight
-constexpr int RING = 4;      // p_new planes kept
-constexpr int kTxBytes = 2 * BOX * 8;
-constexpr int kSmemBytes = S * 2 * BOXB + RING * BOXB + S * 8 + 128;
+constexpr int TY = 8;     // tile rows
+constexpr int S = 3;      // TMA stages in flight
+constexpr int RING = 4;   // p_new planes kept
+
+// Tile configuration: TX cells along x, TX/2 lanes x 4 row-pairs = 2*TX threads.
+//   TX=128: 256 threads, 104 KB shared memory, 2 CTAs per SM
+//   TX=64 : 128 threads,  54 KB shared memory, 4 CTAs per SM (more independent
+//           phases per SM to overlap one CTA's barrier/compute with another's loads)
+template <int TX_>
+struct Cfg {
+  static constexpr int TX = TX_;
+  static constexpr int NT = 2 * TX;
+  static constexpr int LXN = TX / 2;  // threads along x
+  static constexpr int MINB = TX == 128 ? 2 : 4;
+  static constexpr int BW = TX + 4;   // box width: x0-2 .. x0+TX+1 (inner pairs 16-byte aligned)
+  static constexpr int BH = TY + 2;   // box height: y0-1 .. y0+TY
+  static constexpr int BOX = BW * BH;                        // doubles per box
+  static constexpr int BOXB = (BOX * 8 + 127) / 128 * 128;   // bytes, 128-aligned for TMA
+  static constexpr int kTxBytes = 2 * BOX * 8;
+  static constexpr int kSmemBytes = S * 2 * BOXB + RING * BOXB + S * 8 + 128;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -71,12 +81,19 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
-template <bool kSingle>
-__global__ void __launch_bounds__(NT, 2)
+// kSym: the matrix is exactly symmetric (checked at upload), so the coefficient
+// towards the upper neighbour is read as the lower coefficient OF that
+// neighbour: 4 coefficient streams instead of 7 (x+ comes from the next lane by
+// warp shuffle, y+ from the next row, z+ is carried in registers to become z- of
+// the next plane).
+template <int TXT, bool kSingle, bool kSym>
+__global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
     k_dir_spmv_tma(const Geom g, const DevPtrs d, const int zc,
                    const __grid_constant__ CUtensorMap map_r,
                    const __grid_constant__ CUtensorMap map_p0,
                    const __grid_constant__ CUtensorMap map_p1) {
+  using C = Cfg<TXT>;
+  constexpr int TX = C::TX, NT = C::NT, BW = C::BW, BOX = C::BOX, BOXB = C::BOXB;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double sm_red[32];
   __shared__ int sm_flag;
@@ -107,7 +124,7 @@ __global__ void __launch_bounds__(NT, 2)
   const int c0 = kGhostX + x0 - 2, c1 = y0;  // row index 1+(y0-1)
   auto issue = [&](int n) {
     const int s = n % S;
-    mbar_arrive_expect_tx(&full[s], kTxBytes);
+    mbar_arrive_expect_tx(&full[s], C::kTxBytes);
     tma_load_3d(stage_r(s), &map_r, &full[s], c0, c1, k0 + n);  // plane index 1+(k0-1+n)
     tma_load_3d(stage_p(s), map_po, &full[s], c0, c1, k0 + n);
   };
@@ -121,15 +138,16 @@ __global__ void __launch_bounds__(NT, 2)
     for (int n = 0; n < S && n < np; ++n) issue(n);
   }
 
-  // cells of this thread: pair (2*lx, 2*lx+1) in rows ly and ly+4 of the tile
-  const int lx = tid & 63, ly = tid >> 6;
+  // cells of this thread: pair (2*lx, 2*lx+1) in rows 2*ly and 2*ly+1 of the tile
+  const int lx = tid % C::LXN, ly = tid / C::LXN;
+  const int lane = tid & 31;
   const int ci = x0 + 2 * lx;
   const bool act_x = ci < g.nx;
   bool act[2];
   int cj[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    cj[h] = y0 + ly + 4 * h;
+    cj[h] = y0 + 2 * ly + h;
     act[h] = act_x && cj[h] < g.ny;
   }
   // ownership of box columns/rows for the p_new stores (interior + face ghosts)
@@ -139,6 +157,8 @@ __global__ void __launch_bounds__(NT, 2)
   const int own_yhi = min(y0 + TY, g.ny) + (y0 + TY >= g.ny ? 1 : 0);
 
   double acc = 0.0;
+  Vec<2> zcarry[2];
+  zcarry[0].v[0] = zcarry[0].v[1] = zcarry[1].v[0] = zcarry[1].v[1] = 0.0;
   for (int n = 0; n < np; ++n) {
     const int z = k0 - 1 + n;  // plane whose p_new is formed in this step
     const int m = z - 1;       // plane whose stencil is evaluated in this step
@@ -148,13 +168,57 @@ __global__ void __launch_bounds__(NT, 2)
     // -- issue the read-once streams of this step before any waiting ---------------
     Vec<2> a[2][7];
     Vec<2> uu[2];
+    if constexpr (!kSym) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (do_stencil && act[h]) {
+          const int64_t idc = ci + cj[h] * g.cy + (int64_t)m * g.cz;
+#pragma unroll
+          for (int q = 0; q < 7; ++q) a[h][q] = ldv_stream<2>(d.a[q] + idc);
+        }
+      }
+    } else {
+      // a[h][1], a[h][3], a[h][5] <- lower coefficients of the own cells;
+      // a[h][2], a[h][4], a[h][6] <- lower coefficients of the upper neighbours
+      Vec<2> zero2;
+      zero2.v[0] = zero2.v[1] = 0.0;
+      a[0][1] = a[1][1] = zero2;
+      if (do_stencil) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (act[h]) {
+            const int64_t idc = ci + cj[h] * g.cy + (int64_t)m * g.cz;
+            a[h][0] = ldv_stream<2>(d.a[0] + idc);
+            a[h][1] = ldv_stream<2>(d.a[1] + idc);
+            a[h][3] = (h == 1) ? a[0][4] : ldv_stream<2>(d.a[3] + idc);
+            // y+: next row's y-, or this row's own y+ on the last row of the domain
+            a[h][4] = (cj[h] + 1 < g.ny) ? ldv<2>(d.a[3] + idc + g.cy) : ldv_stream<2>(d.a[4] + idc);
+            // z-: carried from the previous plane (its z+), except on the first plane
+            a[h][5] = (n == 2) ? ldv_stream<2>(d.a[5] + idc) : zcarry[h];
+            a[h][6] = (m + 1 < g.nzl) ? ldv_stream<2>(d.a[5] + idc + g.cz) : ldv_stream<2>(d.a[6] + idc);
+            zcarry[h] = a[h][6];
+          }
+        }
+        // x+ of the second cell of the pair = x- of the next lane's first cell
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double from_next = __shfl_down_sync(0xffffffffu, a[h][1].v[0], 1);
+          if (act[h]) {
+            const int64_t idc = ci + cj[h] * g.cy + (int64_t)m * g.cz;
+            a[h][2].v[0] = a[h][1].v[1];
+            if (ci + 2 >= g.nx) {
+              a[h][2].v[1] = d.a[2][idc + 1];  // last cell of the row: its own x+
+            } else if (lane == 31) {
+              a[h][2].v[1] = d.a[1][idc + 2];  // next lane lives in another warp / CTA
+            } else {
+              a[h][2].v[1] = from_next;
+            }
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (do_stencil && act[h]) {
-        const int64_t idc = ci + cj[h] * g.cy + (int64_t)m * g.cz;
-#pragma unroll
-        for (int q = 0; q < 7; ++q) a[h][q] = ldv_stream<2>(d.a[q] + idc);
-      }
       if (z_inner && act[h]) {
         uu[h] = ldv_stream<2>(d.u + ci + cj[h] * g.cy + (int64_t)z * g.cz);
       }
@@ -197,7 +261,7 @@ __global__ void __launch_bounds__(NT, 2)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (act[h]) {
-          const int o = (ly + 4 * h + 1) * BW + 2 + 2 * lx;
+          const int o = (2 * ly + h + 1) * BW + 2 + 2 * lx;
           const double2 pv = *reinterpret_cast<const double2*>(sp + o);
           uu[h].v[0] = fma(alpha_prev, pv.x, uu[h].v[0]);
           uu[h].v[1] = fma(alpha_prev, pv.y, uu[h].v[1]);
@@ -216,7 +280,7 @@ __global__ void __launch_bounds__(NT, 2)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (act[h]) {
-          const int o = (ly + 4 * h + 1) * BW + 2 + 2 * lx;
+          const int o = (2 * ly + h + 1) * BW + 2 + 2 * lx;
           const double2 pc = *reinterpret_cast<const double2*>(rc + o);
           const double pxm = rc[o - 1], pxp = rc[o + 2];
           const double2 pym = *reinterpret_cast<const double2*>(rc + o - BW);
@@ -273,7 +337,21 @@ struct TmaPlan {
   alignas(64) CUtensorMap map_r, map_p0, map_p1;
   dim3 grid;
   int zc;
+  int tx;  // tile width in use (64 or 128)
 };
+
+template <int TXT>
+static bool set_smem_limit() {
+  using C = Cfg<TXT>;
+  return cudaFuncSetAttribute(k_dir_spmv_tma<TXT, true, false>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess &&
+         cudaFuncSetAttribute(k_dir_spmv_tma<TXT, false, false>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess &&
+         cudaFuncSetAttribute(k_dir_spmv_tma<TXT, true, true>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess &&
+         cudaFuncSetAttribute(k_dir_spmv_tma<TXT, false, true>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess;
+}
 
 TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen) {
   auto fail = [&](const char* msg) -> TmaPlan* {
@@ -290,9 +368,13 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
     return fail("cuTensorMapEncodeTiled not available");
   }
   TmaPlan* p = new TmaPlan();
+  p->tx = (g.nx <= 64) ? 64 : 128;
+  if (const char* et = getenv("APHCG_TILE")) p->tx = (atoi(et) == 64) ? 64 : 128;
+  const int TX = p->tx;
+  const int BW = TX + 4, BH = TY + 2;
   const cuuint64_t gdim[3] = {(cuuint64_t)g.py, (cuuint64_t)(g.ny + 2), (cuuint64_t)(g.nzl + 2)};
   const cuuint64_t gstr[2] = {(cuuint64_t)g.py * 8, (cuuint64_t)g.pz * 8};
-  const cuuint32_t box[3] = {BW, BH, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)BW, (cuuint32_t)BH, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   double* bases[3] = {d.r, d.p[0], d.p[1]};
   CUtensorMap* maps[3] = {&p->map_r, &p->map_p0, &p->map_p1};
@@ -317,10 +399,7 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
   if (zc > g.nzl) zc = g.nzl;
   p->zc = zc;
   p->grid = dim3((g.nx + TX - 1) / TX, (g.ny + TY - 1) / TY, (g.nzl + zc - 1) / zc);
-  if (cudaFuncSetAttribute(k_dir_spmv_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kSmemBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(k_dir_spmv_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kSmemBytes) != cudaSuccess) {
+  if (!(TX == 64 ? set_smem_limit<64>() : set_smem_limit<128>())) {
     cudaGetLastError();
     delete p;
     return fail("cannot raise the dynamic shared memory limit");
@@ -331,14 +410,27 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
 void tma_plan_destroy(TmaPlan* p) { delete p; }
 unsigned tma_plan_blocks(const TmaPlan* p) { return p->grid.x * p->grid.y * p->grid.z; }
 
-void launch_dir_spmv_tma(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool single,
-                         cudaStream_t s) {
+template <int TXT>
+static void launch_cfg(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool single, bool sym,
+                       cudaStream_t s) {
+  using C = Cfg<TXT>;
+#define APHCG_LAUNCH_TMA(SINGLE, SYM)                                                    \
+  k_dir_spmv_tma<TXT, SINGLE, SYM><<<p->grid, C::NT, C::kSmemBytes, s>>>(g, d, p->zc, p->map_r, \
+                                                                         p->map_p0, p->map_p1)
   if (single) {
-    k_dir_spmv_tma<true><<<p->grid, NT, kSmemBytes, s>>>(g, d, p->zc, p->map_r, p->map_p0,
-                                                         p->map_p1);
+    if (sym) APHCG_LAUNCH_TMA(true, true); else APHCG_LAUNCH_TMA(true, false);
   } else {
-    k_dir_spmv_tma<false><<<p->grid, NT, kSmemBytes, s>>>(g, d, p->zc, p->map_r, p->map_p0,
-                                                          p->map_p1);
+    if (sym) APHCG_LAUNCH_TMA(false, true); else APHCG_LAUNCH_TMA(false, false);
+  }
+#undef APHCG_LAUNCH_TMA
+}
+
+void launch_dir_spmv_tma(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool single, bool sym,
+                         cudaStream_t s) {
+  if (p->tx == 64) {
+    launch_cfg<64>(p, g, d, single, sym, s);
+  } else {
+    launch_cfg<128>(p, g, d, single, sym, s);
   }
 }
 

@@ -44,8 +44,10 @@ enum {
                                 src/linear/linear.ipp:103-107,245-249) */
   APHCG_NO_GRAPH = 1u << 1,  /* launch kernels one by one instead of replaying
                                 a CUDA graph (debugging) */
-  APHCG_NO_TMA = 1u << 2     /* use the plain-load stencil kernel instead of the
+  APHCG_NO_TMA = 1u << 2,    /* use the plain-load stencil kernel instead of the
                                 TMA-staged one (debugging / comparison) */
+  APHCG_NO_SYM = 1u << 3     /* always stream all 7 coefficient arrays, even when
+                                the resident matrix is verified symmetric */
 };
 
 typedef struct aphcg aphcg_t;

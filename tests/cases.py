@@ -28,6 +28,19 @@ def random_guess(shape, seed=3):
     return np.random.default_rng(seed).standard_normal(shape)
 
 
+def initial_residual(system, x0, periodic):
+    """sqrt(sum r0^2 / V), r0 = -(A x0 + e7): the residual of the guess in the
+    reference's norm (src/linear/linear.ipp:48-56,103-107); tolerances "relative to
+    the start" are expressed through it because the reference only knows absolute
+    ones."""
+    from oracle import cpu
+    shape = system.shape[:3]
+    r0 = system[..., 7].copy()
+    if x0 is not None:
+        r0 = r0 + cpu.apply(system, x0, periodic=periodic)
+    return float(np.sqrt((r0 ** 2).sum() / systems.cell_volume(shape)))
+
+
 def rel_max_abs(a, b):
     """The parity measure of the north star: max|a-b| / max|b|."""
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))

@@ -1,0 +1,91 @@
+"""Multi-GPU parity (needs >= 2 GPUs: `gpurun --gpus 2`): z-slabs on separate
+processes, residual ghost planes written into the neighbour GPU's memory over
+NVLink, scalars all-reduced with NCCL; compared with the single-domain oracle."""
+
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from aphros_b200 import capi
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np
+import torch, torch.distributed as dist
+from aphros_b200 import Conf, SolverConjugateCuda, distr, systems
+from cases import initial_residual, rel_max_abs
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+from oracle import cpu
+ok = True
+for name in ["tlinear_periodic", "density_walls", "uneven"]:
+    if name == "tlinear_periodic":
+        shape, per = (32, 32, 32), (True, True, True)
+        s, _ = systems.tlinear_system(32)
+    elif name == "density_walls":
+        shape, per = (48, 32, 64), (False, False, False)
+        s, _ = systems.density_poisson_system(None, nspheres=6, seed=4, rho_in=0.05, shape=shape)
+    else:
+        shape, per = (world * 5 + 1, 12, 130), (True, True, True)
+        s, _ = systems.tlinear_system(None, shape=shape)
+    x0 = np.random.default_rng(1).standard_normal(shape) * 1e-3
+    tol = 1e-9 * initial_residual(s, x0, per)
+    conf = Conf(tol=tol, miniter=0, maxiter=3000)
+    m = distr.local_mesh(shape, per, rank, world, device=rank)
+    solver = SolverConjugateCuda(conf, {}, m)
+    distr.connect(solver)
+    sl = slice(m.z0, m.z0 + m.nz_local)
+    x = np.zeros(m.local_shape)
+    info = solver.Solve(np.ascontiguousarray(s[sl]), np.ascontiguousarray(x0[sl]), x)
+    xo, it_o, res_o, _ = cpu.solve(s, x0, periodic=per, tol=tol, miniter=0, maxiter=3000)
+    err = rel_max_abs(x, xo[sl]) * np.abs(xo[sl]).max() / np.abs(xo).max()
+    # second solve on the same handle: zero guess, fixed iteration count
+    solver.SetConf(Conf(tol=0.0, miniter=0, maxiter=30))
+    x2 = np.zeros(m.local_shape)
+    info2 = solver.Solve(np.ascontiguousarray(s[sl]), None, x2)
+    xo2, it_o2, res_o2, _ = cpu.solve(s, None, periodic=per, tol=0.0, miniter=0, maxiter=30)
+    good = (abs(info.iter - it_o) <= 2 + it_o // 100 and err <= 1e-9 and info2.iter == it_o2
+            and abs(info2.residual - res_o2) <= 1e-7 * res_o2)
+    print("rank %%d %%s: iter %%d/%%d err %%.2e | iter %%d/%%d res %%.6e/%%.6e %%s" %% (
+        rank, name, info.iter, it_o, err, info2.iter, it_o2, info2.residual, res_o2,
+        "OK" if good else "FAIL"), flush=True)
+    ok = ok and good
+    solver.close()
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+"""
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slabs_match_single_domain_oracle(gpu, tmp_path, world):
+    if capi.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29600 + world),
+               WORLD_SIZE=str(world))
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(world)]
+    outs = []
+    for p in procs:
+        try:
+            outs.append(p.communicate(timeout=600)[0])
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            pytest.fail("multi-GPU worker timed out")
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d failed:\n%s" % (r, o[-3000:])

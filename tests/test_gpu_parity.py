@@ -39,7 +39,8 @@ def compare_solutions(case, x, xo):
     return rel_max_abs(x, xo)
 
 
-VARIANTS = [pytest.param(0, id="tma+graph"),
+VARIANTS = [pytest.param(0, id="tma+sym+graph"),
+            pytest.param(capi.APHCG_NO_SYM, id="tma+7coef+graph"),
             pytest.param(capi.APHCG_NO_TMA, id="plain+graph"),
             pytest.param(capi.APHCG_NO_TMA | capi.APHCG_NO_GRAPH, id="plain+nograph"),
             pytest.param(capi.APHCG_NO_GRAPH, id="tma+nograph")]
@@ -78,7 +79,7 @@ def rhs_norm_of(case):
     return float(np.sqrt((case["system"][..., 7] ** 2).sum() / __import__('aphros_b200').systems.cell_volume(shape)))
 
 
-@pytest.mark.parametrize("flags", VARIANTS[:2])
+@pytest.mark.parametrize("flags", VARIANTS[:3])
 @pytest.mark.parametrize("name", sorted(PARITY_CASES))
 def test_iterations_to_tolerance(gpu, name, flags):
     """iteration count to a 1e-8 relative residual (the north star's setting,
@@ -92,7 +93,7 @@ def test_iterations_to_tolerance(gpu, name, flags):
     assert info.residual < conf.tol
 
 
-@pytest.mark.parametrize("flags", VARIANTS[:2])
+@pytest.mark.parametrize("flags", VARIANTS[:3])
 @pytest.mark.parametrize("name", sorted(PARITY_CASES))
 def test_solution_parity(gpu, name, flags):
     """solution within 1e-10 relative max-abs of the oracle's once both are
@@ -265,3 +266,24 @@ def test_device_assembly_matches_host_generator(gpu):
 
 
 import sys  # noqa: E402
+
+
+def test_nonsymmetric_storage_falls_back(gpu):
+    """a system whose off-diagonals are not bitwise symmetric must take the 7-stream
+    path and still match the oracle (CG itself may not converge on it: compare a fixed
+    number of iterations)"""
+    case = case_tlinear(24)
+    s = case["system"].copy()
+    s[3, 4, 5, 2] *= 1.0 + 2.0 ** -40      # x+ of one cell, no longer equal to its mirror
+    s[7, 0, 9, 4] *= 1.0 - 2.0 ** -41      # y+
+    s[11, 2, 2, 6] *= 1.0 + 2.0 ** -39     # z+
+    case = dict(system=s, periodic=case["periodic"])
+    conf = Conf(tol=0.0, miniter=0, maxiter=40)
+    x, info, hist = gpu_solve(case, conf)
+    xo, it_o, res_o, hist_o = oracle_solve(case, tol=0.0, miniter=0, maxiter=40)
+    assert info.iter == it_o == 41
+    np.testing.assert_allclose(hist, hist_o, rtol=1e-9)
+    assert rel_max_abs(x, xo) < 1e-10
+    # and the perturbation is visible at all: the symmetric path would differ
+    x_sym, _, hist_sym = gpu_solve(dict(system=case_tlinear(24)["system"], periodic=case["periodic"]), conf)
+    assert not np.array_equal(hist_sym, hist)
