@@ -94,9 +94,16 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
                    const __grid_constant__ CUtensorMap map_p1) {
   using C = Cfg<TXT>;
   constexpr int TX = C::TX, NT = C::NT, BW = C::BW, BOX = C::BOX, BOXB = C::BOXB;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // Dynamic shared memory, indexed only through pointers derived from the
+  // __shared__ symbol itself so that every access compiles to LDS/STS (a detour
+  // through an integer cast makes ptxas fall back to generic LD/ST).
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ double sm_red[32];
   __shared__ int sm_flag;
+  constexpr int BOXD = BOXB / 8;  // doubles per staged box (padded to 128 bytes)
+  double* const smd = reinterpret_cast<double*>(smem_raw);
+  // layout: [S x (r box | p_old box)] [RING x p_new box] [S mbarriers]
+  uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + (2 * S + RING) * BOXB);
   CgState* st = d.st;
   if (st->done) return;
   const double beta = cg_beta(st);
@@ -104,15 +111,6 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
   const int par = st->iter & 1;
   const CUtensorMap* map_po = par ? &map_p1 : &map_p0;
   double* __restrict__ pn_glob = d.p[par ^ 1];
-
-  // shared memory carve-up (base is 128-byte aligned by hand: the runtime only
-  // guarantees 16 for dynamic shared memory)
-  unsigned char* base = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  auto stage_r = [&](int s) { return reinterpret_cast<double*>(base + (2 * s) * BOXB); };
-  auto stage_p = [&](int s) { return reinterpret_cast<double*>(base + (2 * s + 1) * BOXB); };
-  auto ring = [&](int s) { return reinterpret_cast<double*>(base + (2 * S + s) * BOXB); };
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + (2 * S + RING) * BOXB);
 
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
@@ -125,8 +123,8 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
   auto issue = [&](int n) {
     const int s = n % S;
     mbar_arrive_expect_tx(&full[s], C::kTxBytes);
-    tma_load_3d(stage_r(s), &map_r, &full[s], c0, c1, k0 + n);  // plane index 1+(k0-1+n)
-    tma_load_3d(stage_p(s), map_po, &full[s], c0, c1, k0 + n);
+    tma_load_3d(smd + (2 * s) * BOXD, &map_r, &full[s], c0, c1, k0 + n);  // plane 1+(k0-1+n)
+    tma_load_3d(smd + (2 * s + 1) * BOXD, map_po, &full[s], c0, c1, k0 + n);
   };
   if (tid == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
@@ -226,9 +224,9 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
 
     const int s = n % S;
     mbar_wait(&full[s], (n / S) & 1);
-    const double* __restrict__ sr = stage_r(s);
-    const double* __restrict__ sp = stage_p(s);
-    double* __restrict__ rg = ring(n % RING);
+    const double* sr = smd + (2 * s) * BOXD;
+    const double* sp = smd + (2 * s + 1) * BOXD;
+    double* rg = smd + (2 * S + n % RING) * BOXD;
 
     // -- (a) p_new = r + beta*p_old on the whole box; store what this CTA owns --------
     const bool z_owned = z_inner || (z == -1 && k0 == 0) || (z == g.nzl && k1 == g.nzl);
@@ -274,9 +272,9 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
 
     // -- (d) stencil of plane m = z-1 from the ring -------------------------------------
     if (do_stencil) {
-      const double* __restrict__ rc = ring((n + RING - 1) % RING);  // plane m
-      const double* __restrict__ rm = ring((n + RING - 2) % RING);  // plane m-1
-      const double* __restrict__ rp = rg;                            // plane m+1
+      const double* rc = smd + (2 * S + (n + RING - 1) % RING) * BOXD;  // plane m
+      const double* rm = smd + (2 * S + (n + RING - 2) % RING) * BOXD;  // plane m-1
+      const double* rp = rg;                                            // plane m+1
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (act[h]) {

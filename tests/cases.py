@@ -41,6 +41,18 @@ def initial_residual(system, x0, periodic):
     return float(np.sqrt((r0 ** 2).sum() / systems.cell_volume(shape)))
 
 
+def iteration_budget(system, x0, periodic, tol, maxiter, blocks=(8, 16, 32)):
+    """(+-2) + the reference's OWN summation-order noise on this system: the spread
+    of the oracle's iteration counts over block sizes (the reference sums per block,
+    so its count moves with the block size: SURVEY.md 0.6 measured 1957 vs 1961 on a
+    1000:1 system).  Near a flat, non-monotone residual curve the count to a
+    tolerance is only defined up to that spread."""
+    from oracle import cpu
+    counts = [cpu.solve(system, x0, periodic=periodic, tol=tol, miniter=0, maxiter=maxiter,
+                        block=b)[1] for b in blocks]
+    return 2 + max(counts) - min(counts), counts
+
+
 def rel_max_abs(a, b):
     """The parity measure of the north star: max|a-b| / max|b|."""
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
