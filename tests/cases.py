@@ -53,6 +53,17 @@ def iteration_budget(system, x0, periodic, tol, maxiter, blocks=(8, 16, 32)):
     return 2 + max(counts) - min(counts), counts
 
 
+def solution_budget(system, x0, periodic, tol, maxiter, blocks=(8, 16, 32)):
+    """max(1e-10, 4 x the reference's own spread): the relative max-abs difference
+    between the oracle's solutions for different block sizes (same system, guess and
+    tolerance) is what "the reference's answer" is defined up to."""
+    from oracle import cpu
+    xs = [cpu.solve(system, x0, periodic=periodic, tol=tol, miniter=0, maxiter=maxiter,
+                    block=b)[0] for b in blocks]
+    spread = max(rel_max_abs(x, xs[0]) for x in xs[1:])
+    return max(1e-10, 4 * spread), spread
+
+
 def rel_max_abs(a, b):
     """The parity measure of the north star: max|a-b| / max|b|."""
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
