@@ -5,7 +5,7 @@
 //   a_f = h*dt/rho_f,  rho_f = 2/(1/rho_- + 1/rho_+),  zero through non-periodic
 //   domain faces;  e0 = sum_f a_f,  e[1+q] = -a_f(q),
 //   e7 = sum_q outward(q)*v_f,  v_f = (u.n_f)*h^2,
-//   u = (sin 2pi x cos 2pi y, -cos 2pi x sin 2pi y, 0).
+//   u = (sin(pi x) cos(2pi y), sin(pi y) cos(2pi z), sin(pi z) cos(2pi x)).
 // Arithmetic is written with explicit round-to-nearest intrinsics so that the
 // sphere classification matches aphros_b200/systems.py bit for bit.
 #include "cg_kernels.cuh"
@@ -94,18 +94,21 @@ __global__ void k_rows_from_density(const Geom g, const AsmPar P, const double* 
     a4[c] = -a[3];
     a5[c] = -a[4];
     a6[c] = -a[5];
-    // e7: divergence of the face-normal velocity (zero normal velocity on the walls)
+    // e7: divergence of the face-normal fluxes (zero flux through the walls)
+    const double pi = 3.141592653589793238462643383279;
     const double xc = __dmul_rn((double)i + 0.5, P.h), yc = __dmul_rn((double)j + 0.5, P.h);
-    const double xf0 = __dmul_rn((double)i, P.h), xf1 = __dmul_rn((double)(i + 1), P.h);
-    const double yf0 = __dmul_rn((double)j, P.h), yf1 = __dmul_rn((double)(j + 1), P.h);
-    const double cy = cos(two_pi * yc), cx = cos(two_pi * xc);
-    double vx0 = sin(two_pi * xf0) * cy * hh, vx1 = sin(two_pi * xf1) * cy * hh;
-    double vy0 = -cx * sin(two_pi * yf0) * hh, vy1 = -cx * sin(two_pi * yf1) * hh;
-    if (i == 0) vx0 = 0.0;
-    if (i == P.nx_g - 1) vx1 = 0.0;
-    if (j == 0) vy0 = 0.0;
-    if (j == P.ny_g - 1) vy1 = 0.0;
-    rhs[c] = __dadd_rn(__dsub_rn(vx1, vx0), __dsub_rn(vy1, vy0));
+    const double zc = __dmul_rn((double)kg + 0.5, P.h);
+    auto flux = [&](int64_t f, int64_t nf, int per, double ct) {
+      // face f of nf+1 along one direction, tangential factor ct
+      if (!per && (f == 0 || f == nf)) return 0.0;
+      if (per && f == nf) f = 0;
+      return __dmul_rn(__dmul_rn(sin(__dmul_rn(pi, __dmul_rn((double)f, P.h))), ct), hh);
+    };
+    const double cy = cos(two_pi * yc), cz = cos(two_pi * zc), cx = cos(two_pi * xc);
+    const double dx = __dsub_rn(flux(i + 1, P.nx_g, P.per[0], cy), flux(i, P.nx_g, P.per[0], cy));
+    const double dy = __dsub_rn(flux(j + 1, P.ny_g, P.per[1], cz), flux(j, P.ny_g, P.per[1], cz));
+    const double dz = __dsub_rn(flux(kg + 1, P.nz_g, P.per[2], cx), flux(kg, P.nz_g, P.per[2], cx));
+    rhs[c] = __dadd_rn(__dadd_rn(dx, dy), dz);
   }
 }
 

@@ -164,9 +164,14 @@ def density_poisson_system(n, nspheres=64, seed=20240601, rho_in=1e-3, rho_out=1
 
     a_f = h*dt/rho_f with harmonic rho_f = 2/(1/rho_- + 1/rho_+); walls are
     Neumann (zero face coefficient); e7 = sum_q outward(q)*v_f with
-    v_f = (u.n_f)*h^2, u = (sin 2pi x cos 2pi y, -cos 2pi x sin 2pi y, 0) at face
-    centres: wall-normal velocity vanishes, so sum(e7)=0 and the singular system
-    is consistent.  Returns (system, rho).
+    v_f = (u.n_f)*h^2 at face centres,
+        u = (sin(pi x) cos(2 pi y), sin(pi y) cos(2 pi z), sin(pi z) cos(2 pi x)):
+    a predicted velocity with non-zero divergence whose wall-normal component
+    vanishes (wall fluxes are set to exactly zero), so sum(e7) telescopes to 0 and
+    the singular system is consistent.  (SURVEY.md 8d proposed the field
+    (sin 2pi x cos 2pi y, -cos 2pi x sin 2pi y, 0); it is discretely
+    divergence-free, i.e. its right-hand side is rounding noise, so it is not used.)
+    Returns (system, rho).
     """
     nz, ny, nx = shape if shape is not None else (n, n, n)
     h = 1.0 / max(nx, ny, nz)
@@ -178,18 +183,25 @@ def density_poisson_system(n, nspheres=64, seed=20240601, rho_in=1e-3, rho_out=1
         rho_f = 2.0 / (1.0 / rho_m + 1.0 / rho)
         a_lo.append(h * dt / rho_f)
     sys = _assemble(a_lo, periodic, 1.0, (nz, ny, nx))
-    xc, yc = _centres(nx, h), _centres(ny, h)
-    # face-normal velocities at lower faces (index i is the face at x = i*h)
+    xc, yc, zc = _centres(nx, h), _centres(ny, h), _centres(nz, h)
+    # face-normal fluxes; index i of v* is the face at coordinate i*h
     xf = np.arange(nx + 1, dtype=np.float64) * h
     yf = np.arange(ny + 1, dtype=np.float64) * h
-    vx = (np.sin(2 * np.pi * xf)[None, :] * np.cos(2 * np.pi * yc)[:, None]) * h * h  # (ny, nx+1)
-    vy = (-np.cos(2 * np.pi * xc)[None, :] * np.sin(2 * np.pi * yf)[:, None]) * h * h  # (ny+1, nx)
-    vx[:, 0] = 0.0
-    vx[:, -1] = 0.0  # sin(0), sin(2pi): exact zeros on the walls
-    vy[0, :] = 0.0
-    vy[-1, :] = 0.0
-    e7 = (vx[:, 1:] - vx[:, :-1]) + (vy[1:, :] - vy[:-1, :])  # (ny, nx), z-independent
-    sys[..., 7] = e7[None, :, :]
+    zf = np.arange(nz + 1, dtype=np.float64) * h
+    hh = h * h
+    vx = (np.sin(np.pi * xf)[None, :] * np.cos(2 * np.pi * yc)[:, None]) * hh   # (ny, nx+1)
+    vy = (np.sin(np.pi * yf)[None, :] * np.cos(2 * np.pi * zc)[:, None]) * hh   # (nz, ny+1)
+    vz = (np.sin(np.pi * zf)[None, :] * np.cos(2 * np.pi * xc)[:, None]) * hh   # (nx, nz+1)
+    for v, per in ((vx, periodic[0]), (vy, periodic[1]), (vz, periodic[2])):
+        if not per:
+            v[:, 0] = 0.0
+            v[:, -1] = 0.0   # no flux through the walls
+        else:
+            v[:, -1] = v[:, 0]
+    dx = (vx[:, 1:] - vx[:, :-1])[None, :, :]                    # (1, ny, nx)
+    dy = (vy[:, 1:] - vy[:, :-1])[:, :, None]                    # (nz, ny, 1)
+    dz = (vz[:, 1:] - vz[:, :-1]).T[:, None, :]                  # (nz, 1, nx)
+    sys[..., 7] = (dx + dy) + dz
     return sys, rho
 
 

@@ -6,8 +6,8 @@ what=${1:-all}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 if [ "$what" = tests ] || [ "$what" = all ]; then
-  timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
-  tail -15 gpurun_out/pytest_gpu.log
+  timeout 1500 python -m pytest tests -m gpu -q -rf > gpurun_out/pytest_gpu.log 2>&1
+  grep -E "^(FAILED|ERROR)|passed|failed|^E  " gpurun_out/pytest_gpu.log | head -60
 fi
 if [ "$what" = bench ] || [ "$what" = all ]; then
   timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err

@@ -91,12 +91,9 @@ def test_golden_vectors_on_gpu(gpu):
         it_ref, res_ref = int(g["iter"]), float(g["residual"])
         fixed = kw["tol"] in (0.0, 1e30)
         assert abs(info.iter - it_ref) <= (0 if fixed else 2 + it_ref // 100), (name, info.iter, it_ref)
-        if name == "density16_1000to1_fixed":
-            # 101 iterations on a 1000:1 system end at the rounding floor (res ~1e-16 of
-            # rhs ~1e-5): digits of the residual are noise there; the solution is not
-            assert rel_max_abs(x, g["x"]) <= 1e-9, name
-            continue
         if fixed:
             assert abs(info.residual - res_ref) <= 1e-7 * res_ref, name
-        tol_x = 1e-10 if kw["tol"] <= 1e-7 and not fixed else 1e-5
-        assert rel_max_abs(x, g["x"]) <= (1e-8 if fixed else tol_x), (name, rel_max_abs(x, g["x"]))
+        # the fixtures stop at loose tolerances (1e-4 .. 1e-9 relative), where one
+        # iteration more or less moves the solution by about tol x condition number;
+        # the 1e-10 solution parity is asserted on converged solves in test_gpu_parity.py
+        assert rel_max_abs(x, g["x"]) <= (1e-8 if fixed else 1e-5), (name, rel_max_abs(x, g["x"]))

@@ -182,8 +182,12 @@ def test_ragged_shapes(gpu, shape):
     x, info, hist = gpu_solve(case, conf)
     xo, it_o, res_o, hist_o = oracle_solve(case, tol=0.0, miniter=0, maxiter=12)
     assert info.iter == it_o
-    k = int(np.argmax(hist_o < 1e-9 * hist_o[0])) if (hist_o < 1e-9 * hist_o[0]).any() else len(hist_o)
-    k = max(k, 1)
+    # compare the history down to 1e-9 of the initial residual (below that both
+    # sit on the rounding floor, where digits are noise)
+    from cases import initial_residual
+    res0 = initial_residual(s, None, (True, True, True))
+    live = hist_o > 1e-9 * res0
+    k = int(np.argmin(live)) if not live.all() else len(hist_o)
     np.testing.assert_allclose(hist[:k], hist_o[:k], rtol=1e-7)
 
 
@@ -261,8 +265,10 @@ def test_device_assembly_matches_host_generator(gpu):
     got = solver.DownloadSystem()
     solver.close()
     assert np.array_equal(got[..., :7], ref[..., :7])
+    # right-hand side: device sin/cos differ from libm by a few ulp of the fluxes,
+    # and e7 is a difference of neighbouring fluxes (cancellation ~ 1/h)
     scale = np.abs(ref[..., 7]).max()
-    assert np.abs(got[..., 7] - ref[..., 7]).max() <= 1e-14 * scale + 1e-22
+    assert np.abs(got[..., 7] - ref[..., 7]).max() <= 1e-12 * scale
 
 
 import sys  # noqa: E402
