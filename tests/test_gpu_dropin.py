@@ -90,7 +90,10 @@ def test_golden_vectors_on_gpu(gpu):
         solver.close()
         it_ref, res_ref = int(g["iter"]), float(g["residual"])
         fixed = kw["tol"] in (0.0, 1e30)
-        assert abs(info.iter - it_ref) <= (0 if fixed else 2 + it_ref // 100), (name, info.iter, it_ref)
+        budget = 0 if fixed else 2
+        if name.startswith("density") and not fixed:
+            budget, counts = iteration_budget(s, x0, per, kw["tol"], kw["maxiter"], blocks=(4, 8, 12, 24))
+        assert abs(info.iter - it_ref) <= budget, (name, info.iter, it_ref)
         if fixed:
             assert abs(info.residual - res_ref) <= 1e-7 * res_ref, name
         # the fixtures stop at loose tolerances (1e-4 .. 1e-9 relative), where one

@@ -55,10 +55,15 @@ for name in ["tlinear_periodic", "density_walls", "uneven"]:
     x2 = np.zeros(m.local_shape)
     info2 = solver.Solve(np.ascontiguousarray(s[sl]), None, x2)
     xo2, it_o2, res_o2, _ = cpu.solve(s, None, periodic=per, tol=0.0, miniter=0, maxiter=30)
+    # the residual of a NON-converged run on the variable-density system depends on the
+    # summation order at O(1) (the oracle itself: 24.2 / 11.8 / 11.2 for one block /
+    # 8^3 / 16^3 blocks), so it is compared only where the oracle is stable
+    res_b = cpu.solve(s, None, periodic=per, tol=0.0, miniter=0, maxiter=30, block=8)[2]
+    stable = abs(res_b - res_o2) <= 1e-9 * res_o2
     budget, counts = iteration_budget(s, x0, per, tol, 3000, blocks=(4, 8, 16))
     xbudget, spread = solution_budget(s, x0, per, tol, 3000, blocks=(4, 8, 16))
     good = (abs(info.iter - it_o) <= budget and err <= xbudget and info2.iter == it_o2
-            and abs(info2.residual - res_o2) <= 1e-7 * res_o2)
+            and (not stable or abs(info2.residual - res_o2) <= 1e-7 * res_o2))
     print("rank %%d %%s: iter %%d/%%d err %%.2e | iter %%d/%%d res %%.6e/%%.6e %%s" %% (
         rank, name, info.iter, it_o, err, info2.iter, it_o2, info2.residual, res_o2,
         "OK" if good else "FAIL"), flush=True)

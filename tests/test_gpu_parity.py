@@ -8,8 +8,8 @@ import numpy as np
 import pytest
 
 from aphros_b200 import Conf, Mesh, SolverConjugateCuda, SolverJacobiCuda, capi
-from cases import (case_density, case_periodic_const, case_tlinear, random_guess, rel_max_abs,
-                   remove_mean)
+from cases import (case_density, case_periodic_const, case_tlinear, iteration_budget,
+                   random_guess, rel_max_abs, remove_mean)
 
 pytestmark = pytest.mark.gpu
 
@@ -83,13 +83,20 @@ def rhs_norm_of(case):
 @pytest.mark.parametrize("name", sorted(PARITY_CASES))
 def test_iterations_to_tolerance(gpu, name, flags):
     """iteration count to a 1e-8 relative residual (the north star's setting,
-    expressed as the absolute tol the reference takes) within +-2"""
+    expressed as the absolute tol the reference takes) within +-2 -- plus, on the
+    variable-density systems, the reference's own summation-order spread (its count
+    moves with the block size there; 0 on the well-conditioned systems)"""
     case = PARITY_CASES[name]()
     conf = Conf(tol=1e-8 * rhs_norm_of(case), miniter=0, maxiter=5000)
     x, info, hist = gpu_solve(case, conf, flags=flags)
     xo, it_o, res_o, hist_o = oracle_solve(case, tol=conf.tol, miniter=0, maxiter=conf.maxiter)
     assert it_o < conf.maxiter, "oracle did not converge: bad test case"
-    assert abs(info.iter - it_o) <= ITER_TOL, (info.iter, it_o)
+    budget = ITER_TOL
+    if name.startswith("density"):
+        budget, counts = iteration_budget(case["system"], None, case["periodic"], conf.tol,
+                                          conf.maxiter, blocks=(4, 8, 16, 32))
+        assert budget <= 12, counts
+    assert abs(info.iter - it_o) <= budget, (info.iter, it_o)
     assert info.residual < conf.tol
 
 
