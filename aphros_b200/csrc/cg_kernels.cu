@@ -16,6 +16,8 @@
 // r and p_old (bitwise the same numbers the owner computes), and ghost layers of
 // r are written by k_update itself -- into this GPU's own ghost cells for
 // periodic wrap, or straight into the neighbour GPU's ghost plane over NVLink.
+#include <cstdlib>
+
 #include "cg_kernels.cuh"
 #include "cg_launch.h"
 
@@ -162,10 +164,11 @@ __global__ void __launch_bounds__(kBX* kBY)
 // every thread keeps kUR independent 128-bit load pairs in flight.
 // ------------------------------------------------------------------------------
 constexpr int kUT = 256;  // threads
-constexpr int kUR = 4;    // rows per thread (loads in flight)
-constexpr int kUZ = 4;    // planes per CTA
 
-template <int VX, bool kSingle>
+// Persistent: the grid is a fixed number of CTAs per SM and every CTA walks over
+// work items (x-chunk, group of UR rows, plane) with a grid stride; each thread keeps
+// UR independent 128-bit load pairs in flight.  Few CTAs -> few partial slots.
+template <int VX, bool kSingle, int UR>
 __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
   __shared__ double sm[32];
   __shared__ int sm_flag;
@@ -173,39 +176,39 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
   if (st->done) return;
   const double alpha = cg_alpha(st);
   double* __restrict__ r = d.r;
-  // x-chunks of kUT*VX cells; blockIdx.x enumerates (x-chunk, row-group)
   const int xchunks = (g.nx + kUT * VX - 1) / (kUT * VX);
-  const int xc = blockIdx.x % xchunks;
-  const int j0 = (blockIdx.x / xchunks) * kUR;
-  const int i = (xc * kUT + threadIdx.x) * VX;
-  const int k0 = blockIdx.y * kUZ;
-  const int k1 = min(k0 + kUZ, g.nzl);
+  const int jgroups = (g.ny + UR - 1) / UR;
+  const int64_t nwork = (int64_t)xchunks * jgroups * g.nzl;
   double acc = 0.0, amax = 0.0;
-  if (i < g.nx) {
-    for (int k = k0; k < k1; ++k) {
-      Vec<VX> ap[kUR], rv[kUR];
+  for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int xc = (int)(w % xchunks);
+    const int64_t t = w / xchunks;
+    const int j0 = (int)(t % jgroups) * UR;
+    const int k = (int)(t / jgroups);
+    const int i = (xc * kUT + threadIdx.x) * VX;
+    if (i >= g.nx) continue;
+    Vec<VX> ap[UR], rv[UR];
 #pragma unroll
-      for (int u = 0; u < kUR; ++u) {
-        const int j = j0 + u;
-        if (j < g.ny) {
-          ap[u] = ldv_stream<VX>(d.ap + i + j * g.cy + k * g.cz);
-          rv[u] = ldv_stream<VX>(r + g.poff + i + j * g.py + k * g.pz);
-        }
+    for (int u = 0; u < UR; ++u) {
+      const int j = j0 + u;
+      if (j < g.ny) {
+        ap[u] = ldv_stream<VX>(d.ap + i + j * g.cy + k * g.cz);
+        rv[u] = ldv_stream<VX>(r + g.poff + i + j * g.py + k * g.pz);
       }
+    }
 #pragma unroll
-      for (int u = 0; u < kUR; ++u) {
-        const int j = j0 + u;
-        if (j < g.ny) {
-          const int64_t idp = g.poff + i + j * g.py + k * g.pz;
+    for (int u = 0; u < UR; ++u) {
+      const int j = j0 + u;
+      if (j < g.ny) {
+        const int64_t idp = g.poff + i + j * g.py + k * g.pz;
 #pragma unroll
-          for (int v = 0; v < VX; ++v) {
-            rv[u].v[v] = fma(-alpha, ap[u].v[v], rv[u].v[v]);  // linear.ipp:89
-            acc = fma(rv[u].v[v], rv[u].v[v], acc);            // :90
-            amax = fmax(amax, fabs(rv[u].v[v]));               // :91
-          }
-          stv<VX>(r + idp, rv[u]);
-          store_images<VX>(g, r, idp, i, j, k, rv[u], d.r_lo_dst, d.r_hi_dst);
+        for (int v = 0; v < VX; ++v) {
+          rv[u].v[v] = fma(-alpha, ap[u].v[v], rv[u].v[v]);  // linear.ipp:89
+          acc = fma(rv[u].v[v], rv[u].v[v], acc);            // :90
+          amax = fmax(amax, fabs(rv[u].v[v]));               // :91
         }
+        stv<VX>(r + idp, rv[u]);
+        store_images<VX>(g, r, idp, i, j, k, rv[u], d.r_lo_dst, d.r_hi_dst);
       }
     }
   }
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
   const double bsum = block_reduce<false>(acc, sm);
   const double bmax = block_reduce<true>(amax, sm);
   const int tid = threadIdx.x;
-  const unsigned nblk = gridDim.x * gridDim.y, bid = blockIdx.x + gridDim.x * blockIdx.y;
+  const unsigned nblk = gridDim.x, bid = blockIdx.x;
   if (tid == 0) {
     d.partials[bid] = bsum;
     d.partials2[bid] = bmax;
@@ -229,9 +232,29 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
   }
 }
 
+static int update_ur() {
+  static int ur = [] {
+    const char* e = getenv("APHCG_UPD_UR");
+    const int v = e ? atoi(e) : 4;
+    return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4;
+  }();
+  return ur;
+}
+static int update_ctas_per_sm() {
+  static int c = [] {
+    const char* e = getenv("APHCG_UPD_CTAS");
+    const int v = e ? atoi(e) : 8;
+    return v >= 1 && v <= 32 ? v : 8;
+  }();
+  return c;
+}
+
 static dim3 update_grid(const Geom& g, int vx) {
+  const int ur = update_ur();
   const int xchunks = (g.nx + kUT * vx - 1) / (kUT * vx);
-  return dim3(xchunks * ((g.ny + kUR - 1) / kUR), (g.nzl + kUZ - 1) / kUZ);
+  const int64_t nwork = (int64_t)xchunks * ((g.ny + ur - 1) / ur) * g.nzl;
+  const int64_t cap = 148 * (int64_t)update_ctas_per_sm();
+  return dim3((unsigned)(nwork < cap ? nwork : cap));
 }
 
 // symmetry check of the off-diagonals inside the slab (see cg_launch.h)
@@ -509,7 +532,7 @@ static dim3 tile_grid(const Geom& g, int vx) {
 unsigned tile_blocks(const Geom& g, int vx) {
   const dim3 gr = tile_grid(g, vx), gu = update_grid(g, vx);
   const unsigned a = gr.x * gr.y * gr.z, b = gu.x * gu.y * gu.z;
-  return a > b ? a : b;
+  return (a > b ? a : b) + 148 * 32;
 }
 
 #define APHCG_DISPATCH_VX(vx, ...) \
@@ -537,13 +560,24 @@ void launch_check_symmetry(const Geom& g, const DevPtrs& d, int* flag, cudaStrea
   k_check_symmetry<<<148 * 8, 256, 0, s>>>(g, d, flag);
 }
 
+template <int VX, int UR>
+static void launch_update_t(const Geom& g, const DevPtrs& d, bool single, dim3 gr, cudaStream_t s) {
+  if (single)
+    k_update<VX, true, UR><<<gr, kUT, 0, s>>>(g, d);
+  else
+    k_update<VX, false, UR><<<gr, kUT, 0, s>>>(g, d);
+}
+
 void launch_update(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s) {
-  const dim3 gr = update_grid(g, vx), bl(kUT);
+  const dim3 gr = update_grid(g, vx);
+  const int ur = update_ur();
   APHCG_DISPATCH_VX(vx, {
-    if (single)
-      k_update<VX, true><<<gr, bl, 0, s>>>(g, d);
-    else
-      k_update<VX, false><<<gr, bl, 0, s>>>(g, d);
+    switch (ur) {
+      case 1: launch_update_t<VX, 1>(g, d, single, gr, s); break;
+      case 2: launch_update_t<VX, 2>(g, d, single, gr, s); break;
+      case 8: launch_update_t<VX, 8>(g, d, single, gr, s); break;
+      default: launch_update_t<VX, 4>(g, d, single, gr, s); break;
+    }
   });
 }
 

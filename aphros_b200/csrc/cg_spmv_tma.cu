@@ -86,9 +86,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // neighbour: 4 coefficient streams instead of 7 (x+ comes from the next lane by
 // warp shuffle, y+ from the next row, z+ is carried in registers to become z- of
 // the next plane).
+// L2 prefetch of one row segment (bytes: multiple of 16), no register or
+// shared-memory cost: lets the HBM->L2 stream of the read-once arrays run `pd`
+// planes ahead of the CTA's compute phase.
+__device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 template <int TXT, bool kSingle, bool kSym>
 __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
-    k_dir_spmv_tma(const Geom g, const DevPtrs d, const int zc,
+    k_dir_spmv_tma(const Geom g, const DevPtrs d, const int zc, const int pd,
                    const __grid_constant__ CUtensorMap map_r,
                    const __grid_constant__ CUtensorMap map_p0,
                    const __grid_constant__ CUtensorMap map_p1) {
@@ -162,6 +169,31 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
     const int m = z - 1;       // plane whose stencil is evaluated in this step
     const bool do_stencil = (n >= 2);
     const bool z_inner = (z >= k0 && z < k1);
+
+    // -- L2 prefetch of the coefficient / x rows `pd` planes ahead ---------------------
+    if (pd > 0) {
+      constexpr int NARR = kSym ? 5 : 8;  // coefficient arrays (+ x) to prefetch
+      if (tid < NARR * TY) {
+        const int arr = tid / TY, row = tid - arr * TY;
+        const int jj = y0 + row;
+        const int w = min(TX, g.nx - x0);
+        // stencil plane of step n+pd is m+pd; x plane is z+pd
+        const int pl = (arr == NARR - 1) ? z + pd : m + pd;
+        const bool ok = jj < g.ny && ((arr == NARR - 1) ? (pl >= k0 && pl < k1)
+                                                        : (pl >= k0 && pl < k1 + (kSym ? 1 : 0) && pl < g.nzl));
+        if (ok) {
+          const double* basep;
+          if (arr == NARR - 1) {
+            basep = d.u;
+          } else if (kSym) {
+            basep = d.a[arr == 0 ? 0 : 2 * arr - 1];  // a0, a1 (x-), a3 (y-), a5 (z-)
+          } else {
+            basep = d.a[arr];
+          }
+          prefetch_l2(basep + x0 + jj * g.cy + (int64_t)pl * g.cz, (unsigned)w * 8u);
+        }
+      }
+    }
 
     // -- issue the read-once streams of this step before any waiting ---------------
     Vec<2> a[2][7];
@@ -335,6 +367,7 @@ struct TmaPlan {
   alignas(64) CUtensorMap map_r, map_p0, map_p1;
   dim3 grid;
   int zc;
+  int pd;  // L2 prefetch distance in planes (0 = off)
   int tx;  // tile width in use (64 or 128)
 };
 
@@ -396,6 +429,8 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
   if (zc < 1) zc = 1;
   if (zc > g.nzl) zc = g.nzl;
   p->zc = zc;
+  p->pd = 2;
+  if (const char* ep = getenv("APHCG_PREFETCH")) p->pd = atoi(ep);
   p->grid = dim3((g.nx + TX - 1) / TX, (g.ny + TY - 1) / TY, (g.nzl + zc - 1) / zc);
   if (!(TX == 64 ? set_smem_limit<64>() : set_smem_limit<128>())) {
     cudaGetLastError();
@@ -413,8 +448,8 @@ static void launch_cfg(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool s
                        cudaStream_t s) {
   using C = Cfg<TXT>;
 #define APHCG_LAUNCH_TMA(SINGLE, SYM)                                                    \
-  k_dir_spmv_tma<TXT, SINGLE, SYM><<<p->grid, C::NT, C::kSmemBytes, s>>>(g, d, p->zc, p->map_r, \
-                                                                         p->map_p0, p->map_p1)
+  k_dir_spmv_tma<TXT, SINGLE, SYM><<<p->grid, C::NT, C::kSmemBytes, s>>>(g, d, p->zc, p->pd,    \
+                                                                         p->map_r, p->map_p0, p->map_p1)
   if (single) {
     if (sym) APHCG_LAUNCH_TMA(true, true); else APHCG_LAUNCH_TMA(true, false);
   } else {

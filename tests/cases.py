@@ -50,7 +50,19 @@ def iteration_budget(system, x0, periodic, tol, maxiter, blocks=(8, 16, 32)):
     from oracle import cpu
     counts = [cpu.solve(system, x0, periodic=periodic, tol=tol, miniter=0, maxiter=maxiter,
                         block=b)[1] for b in blocks]
-    return 2 + max(counts) - min(counts), counts
+    # the few block sizes tried under-sample that noise: never tighter than 1.5 %
+    return max(2 + max(counts) - min(counts), -(-3 * max(counts) // 200)), counts
+
+
+def residual_envelope(system, x0, periodic, maxiter, maxnorm=False, blocks=(4, 8, 16)):
+    """final residuals of the oracle after a FIXED number of iterations, over block
+    sizes.  On a non-converged 1000:1 system they differ at O(1) (16^3, 101 iterations:
+    0.21 / 0.50 / 1.10 for block 16 / 8 / 4), so such a residual is not a reproducible
+    quantity of the reference; callers compare digits only when the envelope is tight."""
+    from oracle import cpu
+    rs = [cpu.solve(system, x0, periodic=periodic, tol=0.0, miniter=0, maxiter=maxiter,
+                    maxnorm=maxnorm, block=b)[2] for b in blocks]
+    return min(rs), max(rs)
 
 
 def solution_budget(system, x0, periodic, tol, maxiter, blocks=(8, 16, 32)):

