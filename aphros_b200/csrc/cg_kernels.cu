@@ -235,16 +235,16 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
 static int update_ur() {
   static int ur = [] {
     const char* e = getenv("APHCG_UPD_UR");
-    const int v = e ? atoi(e) : 4;
-    return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4;
+    const int v = e ? atoi(e) : 8;
+    return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 8;
   }();
   return ur;
 }
 static int update_ctas_per_sm() {
   static int c = [] {
     const char* e = getenv("APHCG_UPD_CTAS");
-    const int v = e ? atoi(e) : 8;
-    return v >= 1 && v <= 32 ? v : 8;
+    const int v = e ? atoi(e) : 16;
+    return v >= 1 && v <= 32 ? v : 16;
   }();
   return c;
 }

@@ -46,12 +46,23 @@ def iteration_budget(system, x0, periodic, tol, maxiter, blocks=(8, 16, 32)):
     of the oracle's iteration counts over block sizes (the reference sums per block,
     so its count moves with the block size: SURVEY.md 0.6 measured 1957 vs 1961 on a
     1000:1 system).  Near a flat, non-monotone residual curve the count to a
-    tolerance is only defined up to that spread."""
+    tolerance is only defined up to that spread.  Returns (budget, counts)."""
     from oracle import cpu
     counts = [cpu.solve(system, x0, periodic=periodic, tol=tol, miniter=0, maxiter=maxiter,
                         block=b)[1] for b in blocks]
-    # the few block sizes tried under-sample that noise: never tighter than 1.5 %
-    return max(2 + max(counts) - min(counts), -(-3 * max(counts) // 200)), counts
+    return 2 + max(counts) - min(counts), counts
+
+
+def iterations_ok(it_gpu, counts):
+    """Iteration parity on an ill-conditioned system, given the oracle's counts for
+    several block sizes: not more than 2 above the reference's slowest configuration,
+    and not more than 3 % (+2) below its fastest.  The asymmetry is deliberate and
+    measured: the CUDA path forms its dot products with pairwise trees and FMAs, i.e.
+    more accurately than the reference's serial sums, and CG's rounding-induced
+    convergence delay shrinks with it -- on every variable-density case here the GPU
+    needs 1-2 % FEWER iterations than any block configuration of the reference
+    (e.g. 1194 vs 1202..1224), never more."""
+    return (it_gpu <= max(counts) + 2) and (it_gpu >= int(0.97 * min(counts)) - 2)
 
 
 def residual_envelope(system, x0, periodic, maxiter, maxnorm=False, blocks=(4, 8, 16)):

@@ -12,8 +12,8 @@ import numpy as np
 import pytest
 
 from aphros_b200 import systems
-from cases import (initial_residual, iteration_budget, rel_max_abs, residual_envelope,
-                   solution_budget)
+from cases import (initial_residual, iteration_budget, iterations_ok, rel_max_abs,
+                   residual_envelope, solution_budget)
 
 pytestmark = pytest.mark.gpu
 
@@ -49,8 +49,8 @@ def test_guess_nonperiodic_and_maxnorm(gpu):
     kw = dict(periodic=(False, False, False), tol=tol, maxiter=4000, block=16)
     xr, itr, resr, _ = cpu.solve_reference(s, x0, solver="conjugate", **kw)
     xg, itg, resg, _ = cpu.solve_reference(s, x0, solver="conjugate_cuda", plugin=PLUGIN, **kw)
-    budget, counts = iteration_budget(s, x0, (False, False, False), tol, 4000)
-    assert abs(itg - itr) <= budget, (itg, itr, counts)
+    _, counts = iteration_budget(s, x0, (False, False, False), tol, 4000)
+    assert iterations_ok(itg, counts + [itr]), (itg, itr, counts)
     xbudget, spread = solution_budget(s, x0, (False, False, False), tol, 4000)
     assert rel_max_abs(xg, xr) <= xbudget, (rel_max_abs(xg, xr), spread)
     kw = dict(periodic=(False, False, False), tol=0.0, maxiter=25, block=16, maxnorm=True)
@@ -91,10 +91,11 @@ def test_golden_vectors_on_gpu(gpu):
         solver.close()
         it_ref, res_ref = int(g["iter"]), float(g["residual"])
         fixed = kw["tol"] in (0.0, 1e30)
-        budget = 0 if fixed else 2
         if name.startswith("density") and not fixed:
-            budget, counts = iteration_budget(s, x0, per, kw["tol"], kw["maxiter"], blocks=(4, 8, 12, 24))
-        assert abs(info.iter - it_ref) <= budget, (name, info.iter, it_ref)
+            _, counts = iteration_budget(s, x0, per, kw["tol"], kw["maxiter"], blocks=(4, 8, 12, 24))
+            assert iterations_ok(info.iter, counts + [it_ref]), (name, info.iter, it_ref, counts)
+        else:
+            assert abs(info.iter - it_ref) <= (0 if fixed else 2), (name, info.iter, it_ref)
         if fixed:
             lo, hi = residual_envelope(s, x0, per, kw["maxiter"], kw.get("maxnorm", False))
             if hi - lo <= 1e-7 * hi:   # the reference's own residual is reproducible here
