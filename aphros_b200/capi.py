@@ -21,6 +21,7 @@ APHCG_MAXNORM = 1 << 0
 APHCG_NO_GRAPH = 1 << 1
 APHCG_NO_TMA = 1 << 2
 APHCG_NO_SYM = 1 << 3
+APHCG_NCCL_REDUCE = 1 << 4
 UNIQUE_ID_BYTES = 128
 IPC_BYTES = 128
 
@@ -89,7 +90,7 @@ SIGNATURES = {
     "aphcg_comm_unique_id": (ctypes.c_int, [_VP]),
     "aphcg_comm_init": (ctypes.c_int, [_VP, _VP]),
     "aphcg_ipc_export": (ctypes.c_int, [_VP, _VP]),
-    "aphcg_ipc_connect": (ctypes.c_int, [_VP, _VP, _VP]),
+    "aphcg_ipc_connect": (ctypes.c_int, [_VP, _VP, ctypes.c_int32]),
     "aphcg_timer_start": (ctypes.c_int, [_VP]),
     "aphcg_timer_stop": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_double)]),
     "aphcg_profile_kernels": (ctypes.c_int, [_VP, ctypes.c_int32, ctypes.POINTER(ctypes.c_double),

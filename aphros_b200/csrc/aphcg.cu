@@ -102,10 +102,11 @@ struct aphcg {
   TmaPlan* tma = nullptr;
   // comm
   ncclComm_t comm = nullptr;
-  void* peer_lo = nullptr;
-  void* peer_hi = nullptr;
-  bool peer_lo_opened = false, peer_hi_opened = false;
+  double* peer[kMaxRanks] = {};        // every rank's slab (own pointer for this rank)
+  bool peer_opened[kMaxRanks] = {};
+  bool use_mail = true;                // scalar all-reduce through peer mailboxes (else NCCL)
   bool connected = false;
+  unsigned long long runs = 0;
   int64_t launches = 0;
   int last_iter = 0;
 };
@@ -141,6 +142,8 @@ void FillDevPtrs(aphcg_t* h) {
   d.partials2 = h->partials2;
   d.r_lo_dst = d.r_hi_dst = nullptr;
   d.p_lo_dst[0] = d.p_lo_dst[1] = d.p_hi_dst[0] = d.p_hi_dst[1] = nullptr;
+  memset(&d.cm, 0, sizeof(d.cm));
+  d.cm.nranks = 1;
 }
 
 // z images when the slab wraps onto itself (one rank, periodic z)
@@ -177,14 +180,18 @@ int EnqueueIteration(aphcg_t* h) {
     launch_dir_spmv_plain(h->g, h->d, h->vx, h->single, h->stream);
   }
   if (!h->single) {
-    if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
-    launch_finish_dir(h->d, h->stream);
+    if (!h->use_mail) {
+      if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
+    }
+    launch_finish_dir(h->d, h->stream);  // with mailboxes: waits for all ranks' partials
   }
   launch_update(h->g, h->d, h->vx, h->single, h->stream);
   if (!h->single) {
-    if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
-    if (h->desc.flags & APHCG_MAXNORM) {
-      if (int rc = AllReduce(h, &h->st->loc_max, ncclMax)) return rc;
+    if (!h->use_mail) {
+      if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
+      if (h->desc.flags & APHCG_MAXNORM) {
+        if (int rc = AllReduce(h, &h->st->loc_max, ncclMax)) return rc;
+      }
     }
     launch_finish_upd(h->d, h->stream);
   }
@@ -312,6 +319,7 @@ int WriteState(aphcg_t* h, const aphcg_conf* conf) {
   s.maxnorm = (h->desc.flags & APHCG_MAXNORM) ? 1 : 0;
   s.cell_volume = h->desc.cell_volume;
   s.hist_cap = h->hist_cap;
+  s.seq_base = (++h->runs) << 32;
   *h->h_st = s;
   CK(cudaMemcpyAsync(h->st, h->h_st, sizeof(CgState), cudaMemcpyHostToDevice, h->stream));
   return 0;
@@ -397,6 +405,7 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
       ds.nz > (1 << 20))
     return Fail(APHCG_ERR_ARG, "bad mesh size %lld x %lld x %lld", (long long)ds.nx,
                 (long long)ds.ny, (long long)ds.nz);
+  if (ds.nranks > kMaxRanks) return Fail(APHCG_ERR_ARG, "at most %d ranks", kMaxRanks);
   if (ds.nranks < 1 || ds.rank < 0 || ds.rank >= ds.nranks)
     return Fail(APHCG_ERR_ARG, "bad rank %d of %d", ds.rank, ds.nranks);
   if (ds.nz_local < 1 || ds.z0 < 0 || ds.z0 + ds.nz_local > ds.nz)
@@ -429,6 +438,7 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
   g.ptotal = g.pz * (g.nzl + 2);
   h->vx = (g.nx % 2 == 0) ? 2 : 1;
   h->use_graph = !(ds.flags & APHCG_NO_GRAPH);
+  if (const char* eg = getenv("APHCG_GRAPH")) h->use_graph = atoi(eg) != 0;
 
   auto cleanup = [&](int rc) {
     aphcg_destroy(h);
@@ -450,8 +460,9 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
   CKC(cudaMalloc(&h->rhs, nb));
   CKC(cudaMalloc(&h->u, nb));
   CKC(cudaMalloc(&h->ap, nb));
-  CKC(cudaMalloc(&h->slab, sizeof(double) * 3 * (size_t)g.ptotal));
-  CKC(cudaMemset(h->slab, 0, sizeof(double) * 3 * (size_t)g.ptotal));
+  const size_t slab_bytes = sizeof(double) * 3 * (size_t)g.ptotal + sizeof(MailSlot) * kMailSlots;
+  CKC(cudaMalloc(&h->slab, slab_bytes));
+  CKC(cudaMemset(h->slab, 0, slab_bytes));
   CKC(cudaMalloc(&h->d_flag, sizeof(int)));
   CKC(cudaMalloc(&h->st, sizeof(CgState)));
   CKC(cudaMemset(h->st, 0, sizeof(CgState)));
@@ -461,6 +472,8 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
   SelfConnect(h);
   // TMA-staged kernel unless disabled or the geometry does not qualify
   h->allow_sym = !(ds.flags & APHCG_NO_SYM);
+  h->use_mail = !(ds.flags & APHCG_NCCL_REDUCE);
+  if (const char* em = getenv("APHCG_ALLREDUCE")) h->use_mail = strcmp(em, "nccl") != 0;
   if (const char* es = getenv("APHCG_SYM")) h->allow_sym = atoi(es) != 0;
   const char* env = getenv("APHCG_SPMV");
   bool want_tma = !(ds.flags & APHCG_NO_TMA);
@@ -495,8 +508,8 @@ int aphcg_destroy(aphcg_t* h) {
   InvalidateGraphs(h);
   if (h->tma) tma_plan_destroy(h->tma);
   if (h->comm) Nccl().CommDestroy(h->comm);
-  if (h->peer_lo_opened) cudaIpcCloseMemHandle(h->peer_lo);
-  if (h->peer_hi_opened) cudaIpcCloseMemHandle(h->peer_hi);
+  for (int q = 0; q < kMaxRanks; ++q)
+    if (h->peer_opened[q]) cudaIpcCloseMemHandle(h->peer[q]);
   for (int q = 0; q < 7; ++q) cudaFree(h->coef[q]);
   cudaFree(h->rhs);
   cudaFree(h->u);
@@ -613,6 +626,9 @@ static int FinishRun(aphcg_t* h, aphcg_info* info) {
   CK(cudaGetLastError());
   h->last_iter = h->h_st->iter;
   h->have_guess = false;  // the guess buffers were consumed
+  if (h->h_st->error)
+    return Fail(APHCG_ERR_COMM, "a peer rank's partial sum did not arrive (iteration %d)",
+                h->h_st->iter);
   if (info) {
     info->residual = h->h_st->residual;
     info->iter = h->h_st->iter;
@@ -826,52 +842,56 @@ int aphcg_ipc_export(aphcg_t* h, void* blob_out) {
   return 0;
 }
 
-int aphcg_ipc_connect(aphcg_t* h, const void* lo_blob, const void* hi_blob) {
+int aphcg_ipc_connect(aphcg_t* h, const void* blobs, int32_t count) {
   if (!h) return Fail(APHCG_ERR_ARG, "null handle");
   if (h->single) return 0;
+  if (!blobs || count != h->desc.nranks)
+    return Fail(APHCG_ERR_ARG, "ipc_connect needs one blob per rank (%d), got %d", h->desc.nranks,
+                (int)count);
   if (int rc = SetDevice(h)) return rc;
   const Geom& g = h->g;
-  IpcBlob lo{}, hi{};
-  if (lo_blob) memcpy(&lo, lo_blob, sizeof(lo));
-  if (hi_blob) memcpy(&hi, hi_blob, sizeof(hi));
-  auto open = [&](const IpcBlob& b, void** out, bool* opened) -> int {
-    if (b.pz != g.pz || b.poff != g.poff)
-      return Fail(APHCG_ERR_COMM, "neighbour slab has a different xy layout");
-    if (b.pid == (int32_t)getpid()) {  // same process: plain peer pointer
-      *out = (void*)(uintptr_t)b.base;
-      *opened = false;
-      return 0;
-    }
-    CK(cudaIpcOpenMemHandle(out, b.handle, cudaIpcMemLazyEnablePeerAccess));
-    *opened = true;
-    return 0;
-  };
-  if (lo_blob) {
-    if (int rc = open(lo, &h->peer_lo, &h->peer_lo_opened)) return rc;
+  const int n = h->desc.nranks, me = h->desc.rank;
+  std::vector<IpcBlob> b(n);
+  for (int q = 0; q < n; ++q) {
+    memcpy(&b[q], (const char*)blobs + (size_t)q * APHCG_IPC_BYTES, sizeof(IpcBlob));
+    if (b[q].rank != q) return Fail(APHCG_ERR_COMM, "blob %d belongs to rank %d", q, b[q].rank);
+    if (b[q].pz != g.pz || b[q].poff != g.poff)
+      return Fail(APHCG_ERR_COMM, "rank %d has a different xy layout", q);
   }
-  if (hi_blob) {
-    if (lo_blob && lo.rank == hi.rank) {  // two ranks, periodic: same neighbour both ways
-      h->peer_hi = h->peer_lo;
-      h->peer_hi_opened = false;
-    } else if (int rc = open(hi, &h->peer_hi, &h->peer_hi_opened)) {
-      return rc;
+  for (int q = 0; q < n; ++q) {
+    if (q == me) {
+      h->peer[q] = h->slab;
+    } else if (b[q].pid == (int32_t)getpid()) {  // same process: plain peer pointer
+      h->peer[q] = (double*)(uintptr_t)b[q].base;
+    } else if (!h->peer[q]) {
+      void* ptr = nullptr;
+      CK(cudaIpcOpenMemHandle(&ptr, b[q].handle, cudaIpcMemLazyEnablePeerAccess));
+      h->peer[q] = (double*)ptr;
+      h->peer_opened[q] = true;
     }
   }
   DevPtrs& d = h->d;
-  if (lo_blob) {  // my bottom plane -> lower neighbour's top ghost plane
-    double* base = (double*)h->peer_lo;
-    const int64_t off = lo.poff + lo.nzl * lo.pz;
-    d.r_lo_dst = base + off;
-    d.p_lo_dst[0] = base + lo.ptotal + off;
-    d.p_lo_dst[1] = base + 2 * lo.ptotal + off;
+  const bool perz = h->desc.periodic[2] != 0;
+  const int lo = me > 0 ? me - 1 : (perz ? n - 1 : -1);
+  const int hi = me < n - 1 ? me + 1 : (perz ? 0 : -1);
+  if (lo >= 0) {  // my bottom plane -> lower neighbour's top ghost plane
+    const int64_t off = b[lo].poff + b[lo].nzl * b[lo].pz;
+    d.r_lo_dst = h->peer[lo] + off;
+    d.p_lo_dst[0] = h->peer[lo] + b[lo].ptotal + off;
+    d.p_lo_dst[1] = h->peer[lo] + 2 * b[lo].ptotal + off;
   }
-  if (hi_blob) {  // my top plane -> upper neighbour's bottom ghost plane
-    double* base = (double*)h->peer_hi;
-    const int64_t off = hi.poff - hi.pz;
-    d.r_hi_dst = base + off;
-    d.p_hi_dst[0] = base + hi.ptotal + off;
-    d.p_hi_dst[1] = base + 2 * hi.ptotal + off;
+  if (hi >= 0) {  // my top plane -> upper neighbour's bottom ghost plane
+    const int64_t off = b[hi].poff - b[hi].pz;
+    d.r_hi_dst = h->peer[hi] + off;
+    d.p_hi_dst[0] = h->peer[hi] + b[hi].ptotal + off;
+    d.p_hi_dst[1] = h->peer[hi] + 2 * b[hi].ptotal + off;
   }
+  // mailboxes live behind the three padded fields of every rank's slab
+  for (int q = 0; q < n; ++q)
+    d.cm.box[q] = reinterpret_cast<MailSlot*>(h->peer[q] + 3 * b[q].ptotal);
+  d.cm.rank = me;
+  d.cm.nranks = n;
+  d.cm.use_mail = h->use_mail ? 1 : 0;
   h->connected = true;
   InvalidateGraphs(h);
   return 0;
@@ -935,9 +955,15 @@ int aphcg_profile_kernels(aphcg_t* h, int32_t iters, double* ms_dir_spmv, double
     sd += a;
     su += b;
   }
-  for (auto& e : ev) cudaEventDestroy(e);
   *ms_dir_spmv = sd / iters;
   *ms_update = su / iters;
+  if (getenv("APHCG_VERBOSE")) {
+    float tot = 0;
+    cudaEventElapsedTime(&tot, ev[0], ev[3 * (size_t)iters - 1]);
+    fprintf(stderr, "aphcg profile: %d iterations, dir %.4f ms + upd %.4f ms = %.4f; span/iter %.4f ms\n",
+            iters, sd / iters, su / iters, (sd + su) / iters, tot / iters);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
   h->launches += 1 + 2 * (int64_t)iters;
   h->have_guess = false;
   return 0;

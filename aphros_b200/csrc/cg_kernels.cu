@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kBX* kBY)
       st->loc_sum = tot;
       if (kSingle) cg_finish_dir(st, tot);
     }
+    if (!kSingle && d.cm.use_mail) mail_push(d.cm, st, 0, tot, 0.0);
   }
 }
 
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
       st->loc_max = mx;
       if (kSingle) cg_finish_upd(st, d.history, tot, mx);
     }
+    if (!kSingle && d.cm.use_mail) mail_push(d.cm, st, 1, tot, mx);
   }
 }
 
@@ -273,13 +275,21 @@ __global__ void k_check_symmetry(const Geom g, const DevPtrs d, int* flag) {
 }
 
 // Multi-GPU: runs after the all-reduce of loc_sum / loc_max.
-__global__ void k_finish_dir(CgState* st) {
+// One warp.  With mailboxes it first waits for every rank's contribution of this
+// step and sums them in rank order; otherwise NCCL has already reduced loc_sum/loc_max.
+__global__ void k_finish_dir(const DevPtrs d) {
+  CgState* st = d.st;
   if (st->done) return;
-  cg_finish_dir(st, st->loc_sum);
+  double sum = st->loc_sum, mx = 0.0;
+  if (d.cm.use_mail && !mail_wait(d.cm, st, 0, &sum, &mx)) return;
+  if (threadIdx.x == 0) cg_finish_dir(st, sum);
 }
-__global__ void k_finish_upd(CgState* st, double* history) {
+__global__ void k_finish_upd(const DevPtrs d) {
+  CgState* st = d.st;
   if (st->done) return;
-  cg_finish_upd(st, history, st->loc_sum, st->loc_max);
+  double sum = st->loc_sum, mx = st->loc_max;
+  if (d.cm.use_mail && !mail_wait(d.cm, st, 1, &sum, &mx)) return;
+  if (threadIdx.x == 0) cg_finish_upd(st, d.history, sum, mx);
 }
 __global__ void k_finish_init(CgState* st) { st->rr = st->loc_sum; }
 
@@ -581,10 +591,8 @@ void launch_update(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStr
   });
 }
 
-void launch_finish_dir(const DevPtrs& d, cudaStream_t s) { k_finish_dir<<<1, 1, 0, s>>>(d.st); }
-void launch_finish_upd(const DevPtrs& d, cudaStream_t s) {
-  k_finish_upd<<<1, 1, 0, s>>>(d.st, d.history);
-}
+void launch_finish_dir(const DevPtrs& d, cudaStream_t s) { k_finish_dir<<<1, 32, 0, s>>>(d); }
+void launch_finish_upd(const DevPtrs& d, cudaStream_t s) { k_finish_upd<<<1, 32, 0, s>>>(d); }
 void launch_finish_init(const DevPtrs& d, cudaStream_t s) { k_finish_init<<<1, 1, 0, s>>>(d.st); }
 void launch_finish_jacobi(const DevPtrs& d, cudaStream_t s) {
   k_finish_jacobi<<<1, 1, 0, s>>>(d.st, d.history);

@@ -109,6 +109,58 @@ __device__ __forceinline__ double reduce_slots(const double* slots, unsigned n, 
   return block_reduce<kMax>(acc, sm);
 }
 
+// ---- peer-memory all-reduce (see cg_types.h) -------------------------------------
+// phase 0: p.Ap (after the direction kernel), phase 1: r.r / max|r| (after the update)
+__device__ __forceinline__ unsigned long long mail_seq(const CgState* st, int phase) {
+  return st->seq_base + 2ull * (unsigned long long)st->iter + (unsigned long long)phase + 1ull;
+}
+// Called by every thread of the CTA that finished the local reduction.
+__device__ __forceinline__ void mail_push(const Comm& cm, const CgState* st, int phase, double sum,
+                                          double mx) {
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  if (tid < cm.nranks) {
+    MailSlot* s = cm.box[tid] + ((phase * 2 + (st->iter & 1)) * kMaxRanks + cm.rank);
+    *reinterpret_cast<volatile double*>(&s->sum) = sum;
+    *reinterpret_cast<volatile double*>(&s->mx) = mx;
+    __threadfence_system();  // values (and this kernel's halo stores) before the flag
+    *reinterpret_cast<volatile unsigned long long*>(&s->seq) = mail_seq(st, phase);
+  }
+}
+// Called by one warp.  Returns false (and flags the error) on timeout.
+__device__ __forceinline__ bool mail_wait(const Comm& cm, CgState* st, int phase, double* sum,
+                                          double* mx) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long want = mail_seq(st, phase);
+  double vs = 0.0, vm = 0.0;
+  bool ok = true;
+  if (lane < cm.nranks) {
+    MailSlot* s = cm.box[cm.rank] + ((phase * 2 + (st->iter & 1)) * kMaxRanks + lane);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned long long*>(&s->seq) != want) {
+      if (clock64() - t0 > 8000000000ll) {  // ~4 s: a peer died; do not hang the GPU
+        ok = false;
+        break;
+      }
+    }
+    __threadfence_system();
+    vs = *reinterpret_cast<volatile double*>(&s->sum);
+    vm = *reinterpret_cast<volatile double*>(&s->mx);
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  double ts = 0.0, tm = 0.0;
+  for (int q = 0; q < cm.nranks; ++q) {  // rank order: the same sum on every rank
+    ts += __shfl_sync(0xffffffffu, vs, q);
+    tm = fmax(tm, __shfl_sync(0xffffffffu, vm, q));
+  }
+  *sum = ts;
+  *mx = tm;
+  if (!ok && lane == 0) {
+    st->error = 1;
+    st->done = 1;
+  }
+  return ok;
+}
+
 // ---- scalar recurrences (reference stages "iter2", "iter3", "check") -----------
 __device__ __forceinline__ double cg_alpha(const CgState* st) {
   return st->rr / (st->pAp + 1e-100);  // linear.ipp:84

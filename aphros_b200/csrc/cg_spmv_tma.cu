@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
       st->loc_sum = tot;
       if (kSingle) cg_finish_dir(st, tot);
     }
+    if (!kSingle && d.cm.use_mail) mail_push(d.cm, st, 0, tot, 0.0);
   }
 }
 

@@ -24,6 +24,27 @@ struct Geom {
   int64_t py, pz, poff, ptotal;
 };
 
+// ---- scalar all-reduce through peer memory ("mailboxes") -----------------------
+// Every rank owns a small array of slots in its own HBM, mapped into every other
+// rank's address space (CUDA IPC).  The CTA that finishes a reduction stores this
+// rank's partial result straight into slot [phase][iteration parity][my rank] of
+// EVERY rank's array (NVLink stores), value first, then -- after a system-scope
+// fence -- a sequence number.  The consumer waits until all nranks sequence numbers
+// of the current step have arrived in its LOCAL array and adds the values in rank
+// order, so every rank forms bitwise the same sum without a collective call.
+constexpr int kMaxRanks = 16;
+struct MailSlot {
+  double sum, mx;
+  unsigned long long seq, pad;
+};
+constexpr int kMailSlots = 2 * 2 * kMaxRanks;  // [phase][parity][source rank]
+struct Comm {
+  MailSlot* box[kMaxRanks];  // box[q]: rank q's slot array (own memory for q == rank)
+  int rank, nranks;
+  int use_mail;  // 1: mailboxes; 0: an NCCL all-reduce on loc_sum/loc_max follows the kernel
+  int pad;
+};
+
 // Loop state; lives in device memory, updated by the kernels themselves so the
 // host never has to read a scalar inside the loop (reference stages
 // "iter2"/"iter3"/"check", src/linear/linear.ipp:83-114).
@@ -47,7 +68,8 @@ struct CgState {
   int done;      // exit rule fired (linear.ipp:110-113); later kernels return at once
   int hist_cap;
   unsigned counter_a, counter_b;  // last-block-done tickets
-  int pad;
+  int error;     // 1: a peer's contribution did not arrive in time (multi-GPU)
+  unsigned long long seq_base;  // distinguishes the mailbox traffic of successive runs
 };
 
 struct DevPtrs {
@@ -69,6 +91,7 @@ struct DevPtrs {
   double* history;
   double* partials;     // one slot per block for sums
   double* partials2;    // one slot per block for max
+  Comm cm;
 };
 
 }  // namespace acg

@@ -95,7 +95,5 @@ def connect(solver, group=None):
     uid = broadcast_bytes(uid, capi.UNIQUE_ID_BYTES, 0, group)
     solver.CommInit(uid)
     blobs = all_gather_bytes(solver.IpcExport(), group)
-    lo, hi = neighbours(m.rank, m.nranks, bool(m.periodic[2]))
-    solver.IpcConnect(blobs[lo] if lo is not None else None,
-                      blobs[hi] if hi is not None else None)
+    solver.IpcConnect(blobs)
     dist.barrier(group)

@@ -244,10 +244,11 @@ class _CudaSolverBase(Solver):
         capi.check(capi.lib().aphcg_ipc_export(self._h, buf))
         return buf.raw
 
-    def IpcConnect(self, lo_blob, hi_blob):
-        lo = ctypes.create_string_buffer(bytes(lo_blob), capi.IPC_BYTES) if lo_blob else None
-        hi = ctypes.create_string_buffer(bytes(hi_blob), capi.IPC_BYTES) if hi_blob else None
-        capi.check(capi.lib().aphcg_ipc_connect(self._h, lo, hi))
+    def IpcConnect(self, blobs):
+        """blobs: every rank's IpcExport() result, ordered by rank"""
+        raw = b"".join(bytes(b).ljust(capi.IPC_BYTES, b"\0") for b in blobs)
+        buf = ctypes.create_string_buffer(raw, len(raw))
+        capi.check(capi.lib().aphcg_ipc_connect(self._h, buf, len(blobs)))
 
 
 class SolverConjugateCuda(_CudaSolverBase):

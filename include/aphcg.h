@@ -46,8 +46,10 @@ enum {
                                 a CUDA graph (debugging) */
   APHCG_NO_TMA = 1u << 2,    /* use the plain-load stencil kernel instead of the
                                 TMA-staged one (debugging / comparison) */
-  APHCG_NO_SYM = 1u << 3     /* always stream all 7 coefficient arrays, even when
+  APHCG_NO_SYM = 1u << 3,    /* always stream all 7 coefficient arrays, even when
                                 the resident matrix is verified symmetric */
+  APHCG_NCCL_REDUCE = 1u << 4 /* multi-GPU: all-reduce the scalars with NCCL instead of
+                                the peer-memory mailboxes (comparison baseline) */
 };
 
 typedef struct aphcg aphcg_t;
@@ -146,21 +148,22 @@ int aphcg_assemble_spheres(
 int aphcg_download_system(aphcg_t* h, double* system, const aphcg_layout* layout);
 
 /* ---- multi-GPU (nranks > 1): one process per GPU -------------------------------
- * Scalars are all-reduced with NCCL; residual halo planes are written straight
- * into the neighbour's ghost planes over NVLink (peer memory), so the two
- * neighbours' buffers must be opened once after create:
+ * Residual halo planes are written straight into the neighbour's ghost planes
+ * over NVLink, and the two scalars per iteration are all-reduced through small
+ * "mailboxes" in every rank's memory, written by the kernel that finishes the
+ * local reduction (peer memory again; NCCL is used once per solve, for the
+ * initial residual and as a barrier).  Wiring, once after create:
  *   1. rank 0: aphcg_comm_unique_id(id); broadcast id to all ranks (the host
  *      harness does this with torch.distributed / MPI / a file);
  *   2. every rank: aphcg_comm_init(h, id)              (collective)
- *   3. every rank: aphcg_ipc_export(h, mine); all-gather the 64-byte blobs;
- *   4. every rank: aphcg_ipc_connect(h, blob[lo], blob[hi])
- *      (lo/hi = neighbour ranks in z; NULL where there is none). */
+ *   3. every rank: aphcg_ipc_export(h, mine); all-gather the 128-byte blobs;
+ *   4. every rank: aphcg_ipc_connect(h, blobs, nranks)  (blobs ordered by rank). */
 #define APHCG_UNIQUE_ID_BYTES 128
 #define APHCG_IPC_BYTES 128
 int aphcg_comm_unique_id(void* id_out);
 int aphcg_comm_init(aphcg_t* h, const void* id);
 int aphcg_ipc_export(aphcg_t* h, void* blob_out);
-int aphcg_ipc_connect(aphcg_t* h, const void* lo_blob, const void* hi_blob);
+int aphcg_ipc_connect(aphcg_t* h, const void* blobs, int32_t count);
 
 /* Device-side timing on the handle's stream (CUDA events): start records an
  * event; stop records another, waits for it and returns the milliseconds between. */

@@ -75,14 +75,17 @@ sys.exit(0 if ok else 1)
 """
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_slabs_match_single_domain_oracle(gpu, tmp_path, world):
+@pytest.mark.parametrize("world,allreduce", [(2, "mail"), (2, "nccl"), (4, "mail"), (8, "mail")])
+def test_slabs_match_single_domain_oracle(gpu, tmp_path, world, allreduce):
+    """allreduce: "mail" = scalars through peer-memory mailboxes written by the kernels
+    (the product path); "nccl" = ncclAllReduce on the same stream (comparison path)"""
     if capi.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT})
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29600 + world),
-               WORLD_SIZE=str(world))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1",
+               MASTER_PORT=str(29600 + world + (50 if allreduce == "nccl" else 0)),
+               WORLD_SIZE=str(world), APHCG_ALLREDUCE=allreduce)
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
              for r in range(world)]
