@@ -95,6 +95,7 @@ SIGNATURES = {
     "aphcg_timer_stop": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_double)]),
     "aphcg_profile_kernels": (ctypes.c_int, [_VP, ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
                                              ctypes.POINTER(ctypes.c_double)]),
+    "aphcg_describe": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.c_int32]),
     "aphcg_stream": (_VP, [_VP]),
     "aphcg_launch_count": (ctypes.c_int64, [_VP]),
     "aphcg_launches_per_iter": (ctypes.c_int, [_VP]),

@@ -969,6 +969,16 @@ int aphcg_profile_kernels(aphcg_t* h, int32_t iters, double* ms_dir_spmv, double
   return 0;
 }
 
+int aphcg_describe(aphcg_t* h, char* buf, int32_t buflen) {
+  if (!h || !buf || buflen < 1) return Fail(APHCG_ERR_ARG, "bad argument");
+  char t[160] = "";
+  if (h->use_tma) tma_plan_describe(h->tma, t, sizeof(t));
+  snprintf(buf, buflen, "spmv=%s%s %s graph=%d allreduce=%s", h->use_tma ? "tma" : "plain",
+           h->use_tma ? (h->sym ? "-sym4" : "-gen7") : "", t, h->use_graph ? 1 : 0,
+           h->single ? "none" : (h->use_mail ? "peer-mailbox" : "nccl"));
+  return 0;
+}
+
 void* aphcg_stream(aphcg_t* h) { return h ? (void*)h->stream : nullptr; }
 int64_t aphcg_launch_count(aphcg_t* h) { return h ? h->launches : 0; }
 int aphcg_launches_per_iter(aphcg_t* h) { return h ? LaunchesPerIter(h) : 0; }

@@ -36,6 +36,7 @@ struct TmaPlan;  // opaque: tensor maps + launch geometry
 TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen);
 void tma_plan_destroy(TmaPlan* p);
 unsigned tma_plan_blocks(const TmaPlan* p);
+void tma_plan_describe(const TmaPlan* p, char* buf, int buflen);
 // sym: read 4 coefficient streams instead of 7 (matrix verified symmetric)
 void launch_dir_spmv_tma(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool single, bool sym,
                          cudaStream_t s);

@@ -443,6 +443,10 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
 
 void tma_plan_destroy(TmaPlan* p) { delete p; }
 unsigned tma_plan_blocks(const TmaPlan* p) { return p->grid.x * p->grid.y * p->grid.z; }
+void tma_plan_describe(const TmaPlan* p, char* buf, int buflen) {
+  snprintf(buf, buflen, "tile=%dx%d planes_per_cta=%d stages=%d l2_prefetch=%d ctas=%u", p->tx, TY,
+           p->zc, S, p->pd, tma_plan_blocks(p));
+}
 
 template <int TXT>
 static void launch_cfg(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool single, bool sym,

@@ -228,6 +228,11 @@ class _CudaSolverBase(Solver):
         capi.check(capi.lib().aphcg_profile_kernels(self._h, iters, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
+    def Describe(self) -> str:
+        buf = ctypes.create_string_buffer(512)
+        capi.check(capi.lib().aphcg_describe(self._h, buf, 512))
+        return buf.value.decode()
+
     def LaunchCount(self):
         return int(capi.lib().aphcg_launch_count(self._h))
 

@@ -250,7 +250,7 @@ def main_ours(args):
         peak, peak_src = peak_hbm_gbs()
         ach = B_ALG_DIR_SPMV * cells_local / (ms_dir * 1e-3) / 1e9
         roofline = {
-            "bound": "hbm", "kernel": "k_dir_spmv_tma", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "bound": "hbm", "kernel": "k_dir_spmv (%s)" % solver.Describe().split(" ")[0], "achieved": ach, "peak": peak, "unit": "GB/s",
             "frac": ach / peak, "traffic": None,
             "algorithmic_bytes_per_launch": B_ALG_DIR_SPMV * cells_local,
             "ms_per_launch": ms_dir, "peak_source": peak_src,
@@ -312,6 +312,7 @@ def main_ours(args):
                 "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2; no flush needed"
                       % (cells_local * 8 * 13 / 1e9),
                 "parallelism": "z-slab x%d" % world,
+                "kernels": solver.Describe(),
             },
             "wall_ms_per_step": wall_ms / args.steps,
             "loop_ms_per_step": loop_ms / args.steps,

@@ -175,6 +175,10 @@ int aphcg_timer_stop(aphcg_t* h, double* ms);
  * kernel and of the update kernel (milliseconds).  Leaves no valid solution. */
 int aphcg_profile_kernels(aphcg_t* h, int32_t iters, double* ms_dir_spmv, double* ms_update);
 
+/* One-line description of the kernel configuration in use (for benchmark
+ * records): stencil kernel variant, tile, prefetch distance, graph, all-reduce. */
+int aphcg_describe(aphcg_t* h, char* buf, int32_t buflen);
+
 /* cudaStream_t the handle enqueues on (as void*), for callers that time with
  * their own events */
 void* aphcg_stream(aphcg_t* h);
