@@ -193,8 +193,12 @@ def main_ours(args):
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
 
     per_gpu = args.size
-    shape = global_shape(world, per_gpu)
-    nsph, seed = SEEDS.get(world, (512 * world, 20240610 + world))
+    if args.strong:  # BASELINE config 3: one size^3 domain cut into N z-slabs
+        shape = (per_gpu, per_gpu, per_gpu)
+        nsph, seed = SEEDS[1]
+    else:
+        shape = global_shape(world, per_gpu)
+        nsph, seed = SEEDS.get(world, (512 * world, 20240610 + world))
     nsph = max(1, int(nsph * (per_gpu / 512.0) ** 3))
     periodic = (False, False, False)
     mesh = distr.local_mesh(shape, periodic, rank, world, device=local_rank)
@@ -302,7 +306,8 @@ def main_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": {
                 "workload": "%dx%dx%d (nz,ny,nx) synthetic variable-density Poisson (S3/S4: %d spheres, "
                             "1000:1 density jump, Neumann walls), %d^3 cells per GPU, z-slabs; one step = "
@@ -341,6 +346,8 @@ def main():
     ap.add_argument("--size", type=int, default=512, help="cells per GPU per direction")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: one size^3 domain over all GPUs (default: size^3 per GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)

@@ -300,3 +300,27 @@ def test_nonsymmetric_storage_falls_back(gpu):
     # and the perturbation is visible at all: the symmetric path would differ
     x_sym, _, hist_sym = gpu_solve(dict(system=case_tlinear(24)["system"], periodic=case["periodic"]), conf)
     assert not np.array_equal(hist_sym, hist)
+
+
+def test_tlinear_cli(gpu, tmp_path, capsys):
+    """the t.linear command line of the reference test (src/test/linear/test:12-16:
+    --tol 1e-5 --maxiter 1000 --verbose --solver <case>) and its acceptance check
+    max_diff_exact < 2*ref + 1e-12 with ref/conjugate/out: max_diff_exact=6.926950e-03"""
+    import re
+    from aphros_b200 import tlinear
+    sysfile = str(tmp_path / "sys.raw")
+    tlinear.main(["--tol", "1e-5", "--maxiter", "1000", "--verbose", "--solver", "conjugate_cuda",
+                  "--system_out", sysfile])
+    out = capsys.readouterr().out
+    got = dict(re.findall(r"(\w+)=(\S+)", out))
+    assert float(got["max_diff_exact"]) < 2 * 6.926950e-03 + 1e-12
+    assert abs(int(got["iter"]) - 122) <= 2            # current reference code: iter=122
+    assert abs(float(got["max_diff_exact"]) - 3.10655e-07) < 1e-10
+    # replay the captured system
+    tlinear.main(["--tol", "1e-5", "--maxiter", "1000", "--verbose", "--solver", "conjugate_cuda",
+                  "--system_in", sysfile])
+    got2 = dict(re.findall(r"(\w+)=(\S+)", capsys.readouterr().out))
+    assert got2["iter"] == got["iter"] and got2["residual"] == got["residual"]
+    tlinear.main(["--tol", "1e-5", "--maxiter", "1000", "--verbose", "--solver", "jacobi_cuda"])
+    got3 = dict(re.findall(r"(\w+)=(\S+)", capsys.readouterr().out))
+    assert abs(int(got3["iter"]) - 613) <= 2
