@@ -22,6 +22,7 @@ APHCG_NO_GRAPH = 1 << 1
 APHCG_NO_TMA = 1 << 2
 APHCG_NO_SYM = 1 << 3
 APHCG_NCCL_REDUCE = 1 << 4
+APHCG_JACOBI_PRECOND = 1 << 5
 UNIQUE_ID_BYTES = 128
 IPC_BYTES = 128
 

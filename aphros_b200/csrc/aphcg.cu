@@ -96,6 +96,9 @@ struct aphcg {
   cudaGraphExec_t gexec_jacobi = nullptr;
   bool use_graph = true;
   bool use_tma = false;
+  bool precond = false;   // opt-in Jacobi-preconditioned recurrence (APHCG_JACOBI_PRECOND)
+  double* rc = nullptr;   // compact residual, preconditioned mode only
+  double* partials3 = nullptr;
   bool sym = false;       // resident matrix verified symmetric -> 4-stream kernel
   bool allow_sym = true;
   int* d_flag = nullptr;
@@ -140,6 +143,8 @@ void FillDevPtrs(aphcg_t* h) {
   d.history = h->history;
   d.partials = h->partials;
   d.partials2 = h->partials2;
+  d.partials3 = h->partials3;
+  d.rc = h->rc;
   d.r_lo_dst = d.r_hi_dst = nullptr;
   d.p_lo_dst[0] = d.p_lo_dst[1] = d.p_hi_dst[0] = d.p_hi_dst[1] = nullptr;
   memset(&d.cm, 0, sizeof(d.cm));
@@ -185,10 +190,13 @@ int EnqueueIteration(aphcg_t* h) {
     }
     launch_finish_dir(h->d, h->stream);  // with mailboxes: waits for all ranks' partials
   }
-  launch_update(h->g, h->d, h->vx, h->single, h->stream);
+  launch_update(h->g, h->d, h->vx, h->single, h->precond, h->stream);
   if (!h->single) {
     if (!h->use_mail) {
       if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
+      if (h->precond) {
+        if (int rc = AllReduce(h, &h->st->loc_sum2, ncclSum)) return rc;
+      }
       if (h->desc.flags & APHCG_MAXNORM) {
         if (int rc = AllReduce(h, &h->st->loc_max, ncclMax)) return rc;
       }
@@ -317,6 +325,7 @@ int WriteState(aphcg_t* h, const aphcg_conf* conf) {
   s.miniter = conf->miniter;
   s.maxiter = conf->maxiter;
   s.maxnorm = (h->desc.flags & APHCG_MAXNORM) ? 1 : 0;
+  s.precond = h->precond ? 1 : 0;
   s.cell_volume = h->desc.cell_volume;
   s.hist_cap = h->hist_cap;
   s.seq_base = (++h->runs) << 32;
@@ -437,6 +446,7 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
   g.poff = kGhostX + g.py + g.pz;
   g.ptotal = g.pz * (g.nzl + 2);
   h->vx = (g.nx % 2 == 0) ? 2 : 1;
+  h->precond = (ds.flags & APHCG_JACOBI_PRECOND) != 0;
   h->use_graph = !(ds.flags & APHCG_NO_GRAPH);
   if (const char* eg = getenv("APHCG_GRAPH")) h->use_graph = atoi(eg) != 0;
 
@@ -490,8 +500,14 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
   }
   CKC(cudaMalloc(&h->partials, sizeof(double) * h->nslots));
   CKC(cudaMalloc(&h->partials2, sizeof(double) * h->nslots));
+  CKC(cudaMalloc(&h->partials3, sizeof(double) * h->nslots));
   h->d.partials = h->partials;
   h->d.partials2 = h->partials2;
+  h->d.partials3 = h->partials3;
+  if (h->precond) {
+    CKC(cudaMalloc(&h->rc, nb));
+    h->d.rc = h->rc;
+  }
   h->hist_cap = 128;
   CKC(cudaMalloc(&h->history, sizeof(double) * h->hist_cap));
   h->d.history = h->history;
@@ -520,6 +536,8 @@ int aphcg_destroy(aphcg_t* h) {
   cudaFree(h->history);
   cudaFree(h->partials);
   cudaFree(h->partials2);
+  cudaFree(h->partials3);
+  cudaFree(h->rc);
   if (h->h_st) cudaFreeHost(h->h_st);
   for (int b = 0; b < 2; ++b) {
     cudaFree(h->stage[b]);
@@ -654,7 +672,7 @@ int aphcg_run(aphcg_t* h, const aphcg_conf* conf, aphcg_info* info) {
   // p_{-1} = 0: the first direction is p = r + 0*0 (linear.ipp:59-62)
   CK(cudaMemsetAsync(h->d.p[0], 0, sizeof(double) * (size_t)h->g.ptotal, h->stream));
   if (int rc = StreamBarrier(h)) return rc;  // neighbours' guess planes have landed
-  launch_init_residual(h->g, h->d, h->vx, h->single, h->stream);
+  launch_init_residual(h->g, h->d, h->vx, h->single, h->precond, h->stream);
   h->launches++;
   if (!h->single) {
     if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
@@ -931,7 +949,7 @@ int aphcg_profile_kernels(aphcg_t* h, int32_t iters, double* ms_dir_spmv, double
   if (int rc = EnsureHistory(h, conf.maxiter)) return rc;
   if (int rc = WriteState(h, &conf)) return rc;
   CK(cudaMemsetAsync(h->d.p[0], 0, sizeof(double) * (size_t)h->g.ptotal, h->stream));
-  launch_init_residual(h->g, h->d, h->vx, true, h->stream);
+  launch_init_residual(h->g, h->d, h->vx, true, h->precond, h->stream);
   std::vector<cudaEvent_t> ev(3 * (size_t)iters);
   for (auto& e : ev) CK(cudaEventCreate(&e));
   for (int i = 0; i < iters; ++i) {
@@ -942,7 +960,7 @@ int aphcg_profile_kernels(aphcg_t* h, int32_t iters, double* ms_dir_spmv, double
       launch_dir_spmv_plain(h->g, h->d, h->vx, true, h->stream);
     }
     CK(cudaEventRecord(ev[3 * i + 1], h->stream));
-    launch_update(h->g, h->d, h->vx, true, h->stream);
+    launch_update(h->g, h->d, h->vx, true, h->precond, h->stream);
     CK(cudaEventRecord(ev[3 * i + 2], h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
@@ -973,8 +991,9 @@ int aphcg_describe(aphcg_t* h, char* buf, int32_t buflen) {
   if (!h || !buf || buflen < 1) return Fail(APHCG_ERR_ARG, "bad argument");
   char t[160] = "";
   if (h->use_tma) tma_plan_describe(h->tma, t, sizeof(t));
-  snprintf(buf, buflen, "spmv=%s%s %s graph=%d allreduce=%s", h->use_tma ? "tma" : "plain",
-           h->use_tma ? (h->sym ? "-sym4" : "-gen7") : "", t, h->use_graph ? 1 : 0,
+  snprintf(buf, buflen, "spmv=%s%s %s precond=%s graph=%d allreduce=%s", h->use_tma ? "tma" : "plain",
+           h->use_tma ? (h->sym ? "-sym4" : "-gen7") : "", t, h->precond ? "jacobi" : "none",
+           h->use_graph ? 1 : 0,
            h->single ? "none" : (h->use_mail ? "peer-mailbox" : "nccl"));
   return 0;
 }

@@ -169,7 +169,10 @@ constexpr int kUT = 256;  // threads
 // Persistent: the grid is a fixed number of CTAs per SM and every CTA walks over
 // work items (x-chunk, group of UR rows, plane) with a grid stride; each thread keeps
 // UR independent 128-bit load pairs in flight.  Few CTAs -> few partial slots.
-template <int VX, bool kSingle, int UR>
+// kPre (opt-in Jacobi preconditioner, z = r/diag): the true residual lives in the
+// compact array d.rc, the padded field d.r carries z (it is what the direction
+// kernel combines with p_old), and the sums are r.z (-> alpha, beta) and r.r (-> norm).
+template <int VX, bool kSingle, int UR, bool kPre>
 __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
   __shared__ double sm[32];
   __shared__ int sm_flag;
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
   if (st->done) return;
   const double alpha = cg_alpha(st);
   double* __restrict__ r = d.r;
+  double acc2 = 0.0;
   const int xchunks = (g.nx + kUT * VX - 1) / (kUT * VX);
   const int jgroups = (g.ny + UR - 1) / UR;
   const int64_t nwork = (int64_t)xchunks * jgroups * g.nzl;
@@ -188,13 +192,19 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
     const int k = (int)(t / jgroups);
     const int i = (xc * kUT + threadIdx.x) * VX;
     if (i >= g.nx) continue;
-    Vec<VX> ap[UR], rv[UR];
+    Vec<VX> ap[UR], rv[UR], dg[UR];
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
       const int j = j0 + u;
       if (j < g.ny) {
-        ap[u] = ldv_stream<VX>(d.ap + i + j * g.cy + k * g.cz);
-        rv[u] = ldv_stream<VX>(r + g.poff + i + j * g.py + k * g.pz);
+        const int64_t idc = i + j * g.cy + k * g.cz;
+        ap[u] = ldv_stream<VX>(d.ap + idc);
+        if (kPre) {
+          rv[u] = ldv_stream<VX>(d.rc + idc);
+          dg[u] = ldv_stream<VX>(d.a[0] + idc);
+        } else {
+          rv[u] = ldv_stream<VX>(r + g.poff + i + j * g.py + k * g.pz);
+        }
       }
     }
 #pragma unroll
@@ -202,35 +212,52 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
       const int j = j0 + u;
       if (j < g.ny) {
         const int64_t idp = g.poff + i + j * g.py + k * g.pz;
+        Vec<VX> zv;
 #pragma unroll
         for (int v = 0; v < VX; ++v) {
           rv[u].v[v] = fma(-alpha, ap[u].v[v], rv[u].v[v]);  // linear.ipp:89
-          acc = fma(rv[u].v[v], rv[u].v[v], acc);            // :90
           amax = fmax(amax, fabs(rv[u].v[v]));               // :91
+          if (kPre) {
+            zv.v[v] = rv[u].v[v] / dg[u].v[v];
+            acc = fma(rv[u].v[v], zv.v[v], acc);             // r.z
+            acc2 = fma(rv[u].v[v], rv[u].v[v], acc2);        // r.r
+          } else {
+            acc = fma(rv[u].v[v], rv[u].v[v], acc);          // :90
+          }
         }
-        stv<VX>(r + idp, rv[u]);
-        store_images<VX>(g, r, idp, i, j, k, rv[u], d.r_lo_dst, d.r_hi_dst);
+        if (kPre) {
+          stv_stream<VX>(d.rc + i + j * g.cy + k * g.cz, rv[u]);
+          stv<VX>(r + idp, zv);
+          store_images<VX>(g, r, idp, i, j, k, zv, d.r_lo_dst, d.r_hi_dst);
+        } else {
+          stv<VX>(r + idp, rv[u]);
+          store_images<VX>(g, r, idp, i, j, k, rv[u], d.r_lo_dst, d.r_hi_dst);
+        }
       }
     }
   }
   if (d.r_lo_dst != nullptr || d.r_hi_dst != nullptr) __threadfence_system();
   const double bsum = block_reduce<false>(acc, sm);
   const double bmax = block_reduce<true>(amax, sm);
+  const double bsum2 = kPre ? block_reduce<false>(acc2, sm) : 0.0;
   const int tid = threadIdx.x;
   const unsigned nblk = gridDim.x, bid = blockIdx.x;
   if (tid == 0) {
     d.partials[bid] = bsum;
     d.partials2[bid] = bmax;
+    if (kPre) d.partials3[bid] = bsum2;
   }
   if (last_block(&st->counter_b, nblk, &sm_flag)) {
     const double tot = reduce_slots<false>(d.partials, nblk, sm);
     const double mx = reduce_slots<true>(d.partials2, nblk, sm);
+    const double tot2 = kPre ? reduce_slots<false>(d.partials3, nblk, sm) : tot;
     if (tid == 0) {
       st->loc_sum = tot;
       st->loc_max = mx;
-      if (kSingle) cg_finish_upd(st, d.history, tot, mx);
+      st->loc_sum2 = tot2;
+      if (kSingle) cg_finish_upd(st, d.history, tot, mx, tot2);
     }
-    if (!kSingle && d.cm.use_mail) mail_push(d.cm, st, 1, tot, mx);
+    if (!kSingle && d.cm.use_mail) mail_push(d.cm, st, 1, tot, mx, tot2);
   }
 }
 
@@ -280,16 +307,16 @@ __global__ void k_check_symmetry(const Geom g, const DevPtrs d, int* flag) {
 __global__ void k_finish_dir(const DevPtrs d) {
   CgState* st = d.st;
   if (st->done) return;
-  double sum = st->loc_sum, mx = 0.0;
-  if (d.cm.use_mail && !mail_wait(d.cm, st, 0, &sum, &mx)) return;
+  double sum = st->loc_sum, mx = 0.0, sum2 = 0.0;
+  if (d.cm.use_mail && !mail_wait(d.cm, st, 0, &sum, &mx, &sum2)) return;
   if (threadIdx.x == 0) cg_finish_dir(st, sum);
 }
 __global__ void k_finish_upd(const DevPtrs d) {
   CgState* st = d.st;
   if (st->done) return;
-  double sum = st->loc_sum, mx = st->loc_max;
-  if (d.cm.use_mail && !mail_wait(d.cm, st, 1, &sum, &mx)) return;
-  if (threadIdx.x == 0) cg_finish_upd(st, d.history, sum, mx);
+  double sum = st->loc_sum, mx = st->loc_max, sum2 = st->precond ? st->loc_sum2 : st->loc_sum;
+  if (d.cm.use_mail && !mail_wait(d.cm, st, 1, &sum, &mx, &sum2)) return;
+  if (threadIdx.x == 0) cg_finish_upd(st, d.history, sum, mx, st->precond ? sum2 : sum);
 }
 __global__ void k_finish_init(CgState* st) { st->rr = st->loc_sum; }
 
@@ -299,7 +326,7 @@ __global__ void k_finish_init(CgState* st) { st->rr = st->loc_sum; }
 // kToPadded: result goes to the padded residual (with ghost copies) and sum r^2
 // is formed; otherwise to a compact array.
 // ------------------------------------------------------------------------------
-template <int VX, bool kInit, bool kSingle>
+template <int VX, bool kInit, bool kSingle, bool kPre = false>
 __global__ void __launch_bounds__(kBX* kBY)
     k_residual(const Geom g, const DevPtrs d, const double* __restrict__ f, double* out) {
   __shared__ double sm[32];
@@ -334,9 +361,20 @@ __global__ void __launch_bounds__(kBX* kBY)
         s = fma(fzm.v[v], a[5].v[v], s);
         s = fma(fzp.v[v], a[6].v[v], s);
         res.v[v] = kInit ? -s : s;
-        acc = fma(res.v[v], res.v[v], acc);
+        if (!kPre) acc = fma(res.v[v], res.v[v], acc);
       }
-      if (kInit) {
+      if (kInit && kPre) {
+        // preconditioned start: r compact, z = r/diag padded, sum r.z
+        Vec<VX> zv;
+#pragma unroll
+        for (int v = 0; v < VX; ++v) {
+          zv.v[v] = res.v[v] / a[0].v[v];
+          acc = fma(res.v[v], zv.v[v], acc);
+        }
+        stv<VX>(d.rc + idc, res);
+        stv<VX>(out + idp, zv);
+        store_images<VX>(g, out, idp, t.i, t.j, k, zv, d.r_lo_dst, d.r_hi_dst);
+      } else if (kInit) {
         stv<VX>(out + idp, res);
         store_images<VX>(g, out, idp, t.i, t.j, k, res, d.r_lo_dst, d.r_hi_dst);
       } else {
@@ -570,23 +608,28 @@ void launch_check_symmetry(const Geom& g, const DevPtrs& d, int* flag, cudaStrea
   k_check_symmetry<<<148 * 8, 256, 0, s>>>(g, d, flag);
 }
 
-template <int VX, int UR>
+template <int VX, int UR, bool kPre>
 static void launch_update_t(const Geom& g, const DevPtrs& d, bool single, dim3 gr, cudaStream_t s) {
   if (single)
-    k_update<VX, true, UR><<<gr, kUT, 0, s>>>(g, d);
+    k_update<VX, true, UR, kPre><<<gr, kUT, 0, s>>>(g, d);
   else
-    k_update<VX, false, UR><<<gr, kUT, 0, s>>>(g, d);
+    k_update<VX, false, UR, kPre><<<gr, kUT, 0, s>>>(g, d);
 }
 
-void launch_update(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s) {
+void launch_update(const Geom& g, const DevPtrs& d, int vx, bool single, bool precond,
+                   cudaStream_t s) {
   const dim3 gr = update_grid(g, vx);
   const int ur = update_ur();
   APHCG_DISPATCH_VX(vx, {
-    switch (ur) {
-      case 1: launch_update_t<VX, 1>(g, d, single, gr, s); break;
-      case 2: launch_update_t<VX, 2>(g, d, single, gr, s); break;
-      case 8: launch_update_t<VX, 8>(g, d, single, gr, s); break;
-      default: launch_update_t<VX, 4>(g, d, single, gr, s); break;
+    if (precond) {
+      launch_update_t<VX, 4, true>(g, d, single, gr, s);
+    } else {
+      switch (ur) {
+        case 1: launch_update_t<VX, 1, false>(g, d, single, gr, s); break;
+        case 2: launch_update_t<VX, 2, false>(g, d, single, gr, s); break;
+        case 4: launch_update_t<VX, 4, false>(g, d, single, gr, s); break;
+        default: launch_update_t<VX, 8, false>(g, d, single, gr, s); break;
+      }
     }
   });
 }
@@ -598,13 +641,21 @@ void launch_finish_jacobi(const DevPtrs& d, cudaStream_t s) {
   k_finish_jacobi<<<1, 1, 0, s>>>(d.st, d.history);
 }
 
-void launch_init_residual(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s) {
+void launch_init_residual(const Geom& g, const DevPtrs& d, int vx, bool single, bool precond,
+                          cudaStream_t s) {
   const dim3 gr = tile_grid(g, vx), bl(kBX, kBY);
   APHCG_DISPATCH_VX(vx, {
-    if (single)
-      k_residual<VX, true, true><<<gr, bl, 0, s>>>(g, d, d.p[1], d.r);
-    else
-      k_residual<VX, true, false><<<gr, bl, 0, s>>>(g, d, d.p[1], d.r);
+    if (precond) {
+      if (single)
+        k_residual<VX, true, true, true><<<gr, bl, 0, s>>>(g, d, d.p[1], d.r);
+      else
+        k_residual<VX, true, false, true><<<gr, bl, 0, s>>>(g, d, d.p[1], d.r);
+    } else {
+      if (single)
+        k_residual<VX, true, true><<<gr, bl, 0, s>>>(g, d, d.p[1], d.r);
+      else
+        k_residual<VX, true, false><<<gr, bl, 0, s>>>(g, d, d.p[1], d.r);
+    }
   });
 }
 

@@ -116,22 +116,23 @@ __device__ __forceinline__ unsigned long long mail_seq(const CgState* st, int ph
 }
 // Called by every thread of the CTA that finished the local reduction.
 __device__ __forceinline__ void mail_push(const Comm& cm, const CgState* st, int phase, double sum,
-                                          double mx) {
+                                          double mx, double sum2 = 0.0) {
   const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
   if (tid < cm.nranks) {
     MailSlot* s = cm.box[tid] + ((phase * 2 + (st->iter & 1)) * kMaxRanks + cm.rank);
     *reinterpret_cast<volatile double*>(&s->sum) = sum;
     *reinterpret_cast<volatile double*>(&s->mx) = mx;
+    *reinterpret_cast<volatile double*>(&s->sum2) = sum2;
     __threadfence_system();  // values (and this kernel's halo stores) before the flag
     *reinterpret_cast<volatile unsigned long long*>(&s->seq) = mail_seq(st, phase);
   }
 }
 // Called by one warp.  Returns false (and flags the error) on timeout.
 __device__ __forceinline__ bool mail_wait(const Comm& cm, CgState* st, int phase, double* sum,
-                                          double* mx) {
+                                          double* mx, double* sum2) {
   const int lane = threadIdx.x & 31;
   const unsigned long long want = mail_seq(st, phase);
-  double vs = 0.0, vm = 0.0;
+  double vs = 0.0, vm = 0.0, v2 = 0.0;
   bool ok = true;
   if (lane < cm.nranks) {
     MailSlot* s = cm.box[cm.rank] + ((phase * 2 + (st->iter & 1)) * kMaxRanks + lane);
@@ -145,15 +146,18 @@ __device__ __forceinline__ bool mail_wait(const Comm& cm, CgState* st, int phase
     __threadfence_system();
     vs = *reinterpret_cast<volatile double*>(&s->sum);
     vm = *reinterpret_cast<volatile double*>(&s->mx);
+    v2 = *reinterpret_cast<volatile double*>(&s->sum2);
   }
   ok = __all_sync(0xffffffffu, ok);
-  double ts = 0.0, tm = 0.0;
+  double ts = 0.0, tm = 0.0, t2 = 0.0;
   for (int q = 0; q < cm.nranks; ++q) {  // rank order: the same sum on every rank
     ts += __shfl_sync(0xffffffffu, vs, q);
     tm = fmax(tm, __shfl_sync(0xffffffffu, vm, q));
+    t2 += __shfl_sync(0xffffffffu, v2, q);
   }
   *sum = ts;
   *mx = tm;
+  *sum2 = t2;
   if (!ok && lane == 0) {
     st->error = 1;
     st->done = 1;
@@ -174,13 +178,16 @@ __device__ __forceinline__ void cg_finish_dir(CgState* st, double pap) { st->pAp
 
 // after the update kernel: global sum r^2 and max|r| are known.
 // Advances the iteration and evaluates the exit rule (linear.ipp:102-113).
+// rr_new: numerator of the next alpha/beta (sum r^2, or sum r.z when preconditioned);
+// rnorm2: sum r^2, the residual norm.
 __device__ __forceinline__ void cg_finish_upd(CgState* st, double* history, double rr_new,
-                                              double max_r) {
+                                              double max_r, double rnorm2) {
   st->alpha_prev = cg_alpha(st);
   st->rr_prev = st->rr;
   st->rr = rr_new;
+  st->rnorm2 = rnorm2;
   st->max_r = max_r;
-  const double res = st->maxnorm ? max_r / st->cell_volume : sqrt(rr_new / st->cell_volume);
+  const double res = st->maxnorm ? max_r / st->cell_volume : sqrt(rnorm2 / st->cell_volume);
   st->residual = res;
   const int it = st->iter + 1;
   if (it - 1 < st->hist_cap) history[it - 1] = res;

@@ -13,12 +13,14 @@ namespace acg {
 unsigned tile_blocks(const Geom& g, int vx);
 
 void launch_dir_spmv_plain(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s);
-void launch_update(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s);
+void launch_update(const Geom& g, const DevPtrs& d, int vx, bool single, bool precond,
+                   cudaStream_t s);
 void launch_finish_dir(const DevPtrs& d, cudaStream_t s);
 void launch_finish_upd(const DevPtrs& d, cudaStream_t s);
 void launch_finish_init(const DevPtrs& d, cudaStream_t s);
 void launch_finish_jacobi(const DevPtrs& d, cudaStream_t s);
-void launch_init_residual(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s);
+void launch_init_residual(const Geom& g, const DevPtrs& d, int vx, bool single, bool precond,
+                          cudaStream_t s);
 void launch_apply(const Geom& g, const DevPtrs& d, int vx, cudaStream_t s);
 void launch_scatter_field(const Geom& g, const double* src, int64_t off, int64_t sy, int64_t sz,
                           double* u, double* fpad, double* lo_dst, double* hi_dst, int vx,

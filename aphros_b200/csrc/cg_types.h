@@ -35,7 +35,8 @@ struct Geom {
 constexpr int kMaxRanks = 16;
 struct MailSlot {
   double sum, mx;
-  unsigned long long seq, pad;
+  unsigned long long seq;
+  double sum2;
 };
 constexpr int kMailSlots = 2 * 2 * kMaxRanks;  // [phase][parity][source rank]
 struct Comm {
@@ -50,8 +51,11 @@ struct Comm {
 // "iter2"/"iter3"/"check", src/linear/linear.ipp:83-114).
 struct CgState {
   // all-reduced scalars
-  double rr;        // sum r^2 of the current residual   (dot_r / next dot_r_prev)
-  double rr_prev;   // sum r^2 before the last update     (dot_r_prev)
+  // rr / rr_prev are the numerators of alpha and beta: sum r^2 in the reference
+  // recurrence, sum r.z (z = r/diag) in the opt-in Jacobi-preconditioned mode
+  double rr;        // current                            (dot_r / next dot_r_prev)
+  double rr_prev;   // before the last update             (dot_r_prev)
+  double rnorm2;    // sum r^2 (the residual norm; equals rr without preconditioner)
   double pAp;       // sum p*Ap                           (dot_p_lp)
   double max_r;     // max |r|
   double alpha_prev;  // alpha of the last completed iteration (x update is deferred
@@ -60,10 +64,12 @@ struct CgState {
   // this rank's partial results, all-reduced in place when nranks > 1
   double loc_sum;
   double loc_max;
+  double loc_sum2;  // preconditioned mode: local sum r^2 (loc_sum holds r.z)
   // Conf (src/linear/linear.h:21-25) + Extra::residual_max
   double tol;
   double cell_volume;
   int miniter, maxiter, maxnorm;
+  int precond;   // 1: Jacobi-preconditioned recurrence (opt-in; not the reference's)
   int iter;      // completed iterations
   int done;      // exit rule fired (linear.ipp:110-113); later kernels return at once
   int hist_cap;
@@ -77,7 +83,8 @@ struct DevPtrs {
   const double* rhs;    // e7, compact
   double* u;            // iterate, compact
   double* ap;           // A*p, compact
-  double* r;            // residual, padded
+  double* r;            // padded: residual r; in preconditioned mode z = r/diag instead
+  double* rc;           // compact true residual (preconditioned mode only)
   double* p[2];         // search direction, padded, ping-pong by iteration parity
   // where this slab's bottom / top inner plane of a padded field must also be
   // stored: the neighbour's ghost plane (peer memory over NVLink when the
@@ -91,6 +98,7 @@ struct DevPtrs {
   double* history;
   double* partials;     // one slot per block for sums
   double* partials2;    // one slot per block for max
+  double* partials3;    // one slot per block for the second sum (preconditioned mode)
   Comm cm;
 };
 

@@ -102,6 +102,8 @@ class _CudaSolverBase(Solver):
         d.rank, d.nranks = m.rank, m.nranks
         d.z0, d.nz_local = m.z0, m.nz_local
         d.flags = flags | (capi.APHCG_MAXNORM if extra.get("residual_max") else 0)
+        if extra.get("jacobi_precond"):
+            d.flags |= capi.APHCG_JACOBI_PRECOND  # opt-in, not the reference's recurrence
         self._h = ctypes.c_void_p()
         capi.check(capi.lib().aphcg_create(ctypes.byref(self._h), ctypes.byref(d)))
 
@@ -310,7 +312,8 @@ class ModuleLinearConjugateCuda(ModuleLinear):
     def Make(self, var, prefix, m):
         # extras follow the "linsolver_<prefix>_<key>" convention (linear.ipp:245-249);
         # read with a default: Vars["k"] throws on a missing key
-        extra = {"residual_max": bool(int(var.get("linsolver_" + prefix + "_maxnorm", 0)))}
+        extra = {"residual_max": bool(int(var.get("linsolver_" + prefix + "_maxnorm", 0))),
+                 "jacobi_precond": bool(int(var.get("linsolver_" + prefix + "_jacobi", 0)))}
         flags = 0
         if int(var.get("linsolver_" + prefix + "_cuda_graph", 1)) == 0:
             flags |= capi.APHCG_NO_GRAPH

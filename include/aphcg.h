@@ -48,8 +48,14 @@ enum {
                                 TMA-staged one (debugging / comparison) */
   APHCG_NO_SYM = 1u << 3,    /* always stream all 7 coefficient arrays, even when
                                 the resident matrix is verified symmetric */
-  APHCG_NCCL_REDUCE = 1u << 4 /* multi-GPU: all-reduce the scalars with NCCL instead of
+  APHCG_NCCL_REDUCE = 1u << 4, /* multi-GPU: all-reduce the scalars with NCCL instead of
                                 the peer-memory mailboxes (comparison baseline) */
+  APHCG_JACOBI_PRECOND = 1u << 5 /* OPT-IN, not the reference's recurrence: conjugate
+                                gradients preconditioned with diag(A) (z = r/e0,
+                                alpha = r.z/p.Ap, beta = r.z_new/r.z, p = z + beta p);
+                                residual and exit rule unchanged (norm of r).  The
+                                reference's SolverConjugate is unpreconditioned, so
+                                iteration counts differ unless diag(A) is constant. */
 };
 
 typedef struct aphcg aphcg_t;

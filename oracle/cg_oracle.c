@@ -212,6 +212,91 @@ int cg_oracle_conjugate(const cg_oracle_desc* d, const double* sys,
   return 0;
 }
 
+int cg_oracle_pconjugate(const cg_oracle_desc* d, const double* sys,
+                         const double* x0, double* x, double* residual,
+                         int* iter_out, double* history) {
+  geom_t g = make_geom(d);
+  double* u = padded_from_compact(&g, x0);
+  double* r = (double*)calloc((size_t)g.ntot, sizeof(double));
+  double* z = (double*)calloc((size_t)g.ntot, sizeof(double));
+  double* p = (double*)calloc((size_t)g.ntot, sizeof(double));
+  double* lp = (double*)calloc((size_t)g.ntot, sizeof(double));
+  if (!u || !r || !z || !p || !lp) {
+    free(u); free(r); free(z); free(p); free(lp);
+    return -1;
+  }
+  fill_ghosts(&g, u);
+  double dot_rz = 0;
+  FOR_BLOCKS(&g) {
+    double b = 0;
+    FOR_CELLS_IN_BLOCK(&g) {
+      const long c = gi(&g, i, j, k);
+      const double* e = row_of(&g, sys, i, j, k);
+      r[c] = -row_apply(&g, e, u, c, 1);
+      z[c] = r[c] / e[0];
+      b += r[c] * z[c];
+    }
+    dot_rz += b;
+  }
+  fill_ghosts(&g, z);
+  memcpy(p, z, (size_t)g.ntot * sizeof(double));
+  int iter = 0;
+  double res = 0;
+  for (;;) {
+    double dot_p_lp = 0;
+    FOR_BLOCKS(&g) {
+      double bp = 0;
+      FOR_CELLS_IN_BLOCK(&g) {
+        const long c = gi(&g, i, j, k);
+        lp[c] = row_apply(&g, row_of(&g, sys, i, j, k), p, c, 0);
+      }
+      FOR_CELLS_IN_BLOCK(&g) {
+        const long c = gi(&g, i, j, k);
+        bp += p[c] * lp[c];
+      }
+      dot_p_lp += bp;
+    }
+    const double alpha = dot_rz / (dot_p_lp + 1e-100);
+    double dot_rz_new = 0, dot_r = 0;
+    double max_r = -1.7976931348623157e308;
+    FOR_BLOCKS(&g) {
+      double bz = 0, br = 0, bm = 0;
+      FOR_CELLS_IN_BLOCK(&g) {
+        const long c = gi(&g, i, j, k);
+        const double* e = row_of(&g, sys, i, j, k);
+        u[c] += alpha * p[c];
+        r[c] -= alpha * lp[c];
+        z[c] = r[c] / e[0];
+        bz += r[c] * z[c];
+        br += r[c] * r[c];
+        const double a = fabs(r[c]);
+        bm = bm > a ? bm : a;
+      }
+      dot_rz_new += bz;
+      dot_r += br;
+      max_r = max_r > bm ? max_r : bm;
+    }
+    const double beta = dot_rz_new / (dot_rz + 1e-100);
+    dot_rz = dot_rz_new;
+    FOR_BLOCKS(&g) {
+      FOR_CELLS_IN_BLOCK(&g) {
+        const long c = gi(&g, i, j, k);
+        p[c] = z[c] + beta * p[c];
+      }
+    }
+    fill_ghosts(&g, p);
+    res = d->maxnorm ? max_r / d->cell_volume : sqrt(dot_r / d->cell_volume);
+    if (history) history[iter] = res;
+    ++iter;
+    if (iter >= d->miniter && (iter > d->maxiter || res < d->tol)) break;
+  }
+  compact_from_padded(&g, u, x);
+  *residual = res;
+  *iter_out = iter;
+  free(u); free(r); free(z); free(p); free(lp);
+  return 0;
+}
+
 int cg_oracle_jacobi(const cg_oracle_desc* d, const double* sys,
                      const double* x0, double* x, double* residual,
                      int* iter_out, double* history) {

@@ -46,6 +46,16 @@ int cg_oracle_conjugate(
     const cg_oracle_desc* d, const double* sys, const double* x0, double* x,
     double* residual, int* iter, double* history);
 
+/* OPT-IN mode of the CUDA module, NOT a reference algorithm ("parity unpinned":
+ * the reference has no preconditioned CG to pin it against): conjugate gradients
+ * preconditioned with diag(A), written in the reference's style (same stages,
+ * same +1e-100 guards, same block-ordered sums, same residual norm and exit rule):
+ *   z = r/e0;  alpha = (r.z)/(p.Ap + 1e-100);  beta = (r.z)_new/((r.z)_old + 1e-100);
+ *   p = z + beta p. */
+int cg_oracle_pconjugate(
+    const cg_oracle_desc* d, const double* sys, const double* x0, double* x,
+    double* residual, int* iter, double* history);
+
 int cg_oracle_jacobi(
     const cg_oracle_desc* d, const double* sys, const double* x0, double* x,
     double* residual, int* iter, double* history);

@@ -45,7 +45,7 @@ def lib():
             build()
         _lib = ctypes.CDLL(LIB_PATH)
         dp = ctypes.POINTER(ctypes.c_double)
-        for name in ("cg_oracle_conjugate", "cg_oracle_jacobi"):
+        for name in ("cg_oracle_conjugate", "cg_oracle_jacobi", "cg_oracle_pconjugate"):
             f = getattr(_lib, name)
             f.restype = ctypes.c_int
             f.argtypes = [ctypes.POINTER(_Desc), dp, dp, dp, dp,
@@ -101,7 +101,8 @@ def solve(system, x0=None, *, periodic=(True, True, True), cell_volume=None, tol
     res = ctypes.c_double()
     it = ctypes.c_int()
     d = _desc(shape, periodic, block, cell_volume, tol, miniter, maxiter, maxnorm)
-    fn = lib().cg_oracle_conjugate if method == "conjugate" else lib().cg_oracle_jacobi
+    fn = {"conjugate": lib().cg_oracle_conjugate, "jacobi": lib().cg_oracle_jacobi,
+          "pconjugate": lib().cg_oracle_pconjugate}[method]
     rc = fn(ctypes.byref(d), _dp(system), _dp(x0c), _dp(x), ctypes.byref(res),
             ctypes.byref(it), _dp(hist))
     if rc != 0:

@@ -324,3 +324,49 @@ def test_tlinear_cli(gpu, tmp_path, capsys):
     tlinear.main(["--tol", "1e-5", "--maxiter", "1000", "--verbose", "--solver", "jacobi_cuda"])
     got3 = dict(re.findall(r"(\w+)=(\S+)", capsys.readouterr().out))
     assert abs(int(got3["iter"]) - 613) <= 2
+
+
+# ---- opt-in Jacobi-preconditioned mode (APHCG_JACOBI_PRECOND) -----------------------
+# Not a reference algorithm (SolverConjugate is unpreconditioned): the
+# checker is our own restatement oracle/cg_oracle.c:cg_oracle_pconjugate ("parity
+# unpinned"), plus the property that it coincides with plain CG when diag(A) is constant.
+
+def gpu_solve_precond(case, conf, x0=None, flags=0):
+    shape = case["system"].shape[:3]
+    solver = SolverConjugateCuda(conf, {"jacobi_precond": True},
+                                 Mesh(shape=shape, periodic=case["periodic"]), flags)
+    x = np.full(shape, np.nan)
+    info = solver.Solve(case["system"], x0, x)
+    hist = solver.History(info.iter)
+    solver.close()
+    return x, info, hist
+
+
+def test_precond_equals_plain_cg_for_constant_diagonal(gpu):
+    case = case_periodic_const(32)
+    conf = Conf(tol=1e-10 * rhs_norm_of(case), miniter=0, maxiter=2000)
+    xp, ip, hp = gpu_solve_precond(case, conf)
+    x, i, h = gpu_solve(case, conf)
+    assert ip.iter == i.iter
+    assert rel_max_abs(xp, x) <= 1e-10
+
+
+@pytest.mark.parametrize("flags", [0, capi.APHCG_NO_TMA], ids=["tma", "plain"])
+def test_precond_matches_its_oracle(gpu, flags):
+    from oracle import cpu
+    for case, x0 in [(case_density(32, rho_in=1e-3), None),
+                     (case_tlinear(32, rho_in=100.0), random_guess((32, 32, 32)))]:
+        from cases import initial_residual
+        tol = 1e-9 * initial_residual(case["system"], x0, case["periodic"])
+        conf = Conf(tol=tol, miniter=0, maxiter=5000)
+        x, info, hist = gpu_solve_precond(case, conf, x0=x0, flags=flags)
+        xo, it_o, res_o, hist_o = cpu.solve(case["system"], x0, periodic=case["periodic"], tol=tol,
+                                            miniter=0, maxiter=5000, method="pconjugate")
+        xc, it_c, _, _ = cpu.solve(case["system"], x0, periodic=case["periodic"], tol=tol,
+                                   miniter=0, maxiter=20000)
+        assert it_o < 5000
+        assert abs(info.iter - it_o) <= 2 + it_o // 50, (info.iter, it_o)
+        assert info.iter < it_c, "the preconditioner should pay off on a variable-density system"
+        n = min(len(hist), len(hist_o), 40)
+        np.testing.assert_allclose(hist[:n], hist_o[:n], rtol=1e-6)
+        assert rel_max_abs(remove_mean(x), remove_mean(xo)) <= 1e-6
