@@ -87,6 +87,8 @@ SIGNATURES = {
     "aphcg_apply": (ctypes.c_int, [_VP, _VP, _PL, _VP, _PL]),
     "aphcg_assemble_spheres": (ctypes.c_int, [_VP, _VP, ctypes.c_int32, ctypes.c_double,
                                               ctypes.c_double, ctypes.c_double]),
+    "aphcg_assemble_projection": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_double,
+                                                 ctypes.c_double]),
     "aphcg_download_system": (ctypes.c_int, [_VP, _VP, _PL]),
     "aphcg_comm_unique_id": (ctypes.c_int, [_VP]),
     "aphcg_comm_init": (ctypes.c_int, [_VP, _VP]),

@@ -802,6 +802,47 @@ int aphcg_assemble_spheres(aphcg_t* h, const double* spheres, int32_t nspheres, 
   return SystemResident(h);
 }
 
+int aphcg_assemble_projection(aphcg_t* h, const double* rho, const double* vx, const double* vy,
+                              const double* vz, const double* source, double dt, double hcell) {
+  if (!h || !rho || !vx || !vy || !vz) return Fail(APHCG_ERR_ARG, "null argument");
+  if (!(dt > 0) || !(hcell > 0)) return Fail(APHCG_ERR_ARG, "dt and h must be positive");
+  if (int rc = SetDevice(h)) return rc;
+  const Geom& g = h->g;
+  const size_t n_rho = (size_t)g.cz * (g.nzl + 2);
+  const size_t n_vx = (size_t)(g.nx + 1) * g.ny * g.nzl;
+  const size_t n_vy = (size_t)g.nx * (g.ny + 1) * g.nzl;
+  const size_t n_vz = (size_t)g.cz * (g.nzl + 1);
+  const size_t n_src = source ? (size_t)g.ncell : 0;
+  double* buf = nullptr;
+  CK(cudaMalloc(&buf, sizeof(double) * (n_rho + n_vx + n_vy + n_vz + n_src)));
+  double* d_rho = buf;
+  double* d_vx = d_rho + n_rho;
+  double* d_vy = d_vx + n_vx;
+  double* d_vz = d_vy + n_vy;
+  double* d_src = source ? d_vz + n_vz : nullptr;
+  auto up = [&](double* dst, const double* src, size_t n) {
+    return cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream);
+  };
+  cudaError_t e = up(d_rho, rho, n_rho);
+  if (e == cudaSuccess) e = up(d_vx, vx, n_vx);
+  if (e == cudaSuccess) e = up(d_vy, vy, n_vy);
+  if (e == cudaSuccess) e = up(d_vz, vz, n_vz);
+  if (e == cudaSuccess && source) e = up(d_src, source, n_src);
+  if (e == cudaSuccess) {
+    int per[3] = {h->desc.periodic[0], h->desc.periodic[1], h->desc.periodic[2]};
+    launch_assemble_faces(g, h->d, h->coef, h->rhs, d_rho, d_vx, d_vy, d_vz, d_src, dt, hcell,
+                          h->desc.cell_volume, h->desc.nz, h->desc.z0, (int)h->desc.nx,
+                          (int)h->desc.ny, per, h->stream);
+    h->launches += 2;
+    e = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(buf);
+  if (e != cudaSuccess) return Fail(APHCG_ERR_CUDA, "assemble failed: %s", cudaGetErrorString(e));
+  CK(cudaGetLastError());
+  h->have_guess = false;
+  return SystemResident(h);
+}
+
 int aphcg_download_system(aphcg_t* h, double* system, const aphcg_layout* layout) {
   if (!h || !system) return Fail(APHCG_ERR_ARG, "null argument");
   if (!h->have_system) return Fail(APHCG_ERR_STATE, "no system resident");

@@ -112,7 +112,97 @@ __global__ void k_rows_from_density(const Geom g, const AsmPar P, const double* 
   }
 }
 
+// ---- general variant: density and face fluxes supplied by the caller ---------------
+// rho_in: (nzl+2, ny, nx) cell densities of planes -1..nzl of this slab (the two extra
+// planes are the z-neighbours' boundary planes; ignored at a non-periodic domain face)
+__global__ void k_pad_density(const Geom g, const AsmPar P, const double* __restrict__ rho_in,
+                              double* rho) {
+  const int64_t nxy = (int64_t)(g.nx + 2) * (g.ny + 2);
+  const int64_t n = nxy * (g.nzl + 2);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int i = (int)(t % (g.nx + 2)) - 1;
+    int j = (int)((t / (g.nx + 2)) % (g.ny + 2)) - 1;
+    const int k = (int)(t / nxy) - 1;
+    const int64_t ip = g.poff + i + (int64_t)j * g.py + (int64_t)k * g.pz;
+    // wrap (periodic) or clamp (wall: the value is multiplied by a zero coefficient)
+    i = P.per[0] ? (i + g.nx) % g.nx : min(max(i, 0), g.nx - 1);
+    j = P.per[1] ? (j + g.ny) % g.ny : min(max(j, 0), g.ny - 1);
+    rho[ip] = rho_in[i + (int64_t)j * g.nx + (int64_t)(k + 1) * g.cz];
+  }
+}
+
+// Rows from the padded density and the caller's face fluxes:
+//   vx (nzl, ny, nx+1), vy (nzl, ny+1, nx), vz (nzl+1, ny, nx); src (nzl, ny, nx) or null.
+// Same face formulas as k_rows_from_density (src/solver/proj.ipp:343-383):
+//   e7 = sum_q outward(q)*v_f - src*V   (proj.ipp:366-378)
+__global__ void k_rows_from_faces(const Geom g, const AsmPar P, const double* __restrict__ rho,
+                                  const double* __restrict__ vx, const double* __restrict__ vy,
+                                  const double* __restrict__ vz, const double* __restrict__ src,
+                                  double vol, double* a0, double* a1, double* a2, double* a3,
+                                  double* a4, double* a5, double* a6, double* rhs) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < g.ncell;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(c % g.nx);
+    const int j = (int)((c / g.nx) % g.ny);
+    const int k = (int)(c / g.cz);
+    const int64_t kg = P.z0 + k;
+    const int64_t ip = g.poff + i + (int64_t)j * g.py + (int64_t)k * g.pz;
+    const double rc = rho[ip];
+    const int64_t off[6] = {-1, 1, -g.py, g.py, -g.pz, g.pz};
+    const bool wall[6] = {!P.per[0] && i == 0,          !P.per[0] && i == P.nx_g - 1,
+                          !P.per[1] && j == 0,          !P.per[1] && j == P.ny_g - 1,
+                          !P.per[2] && kg == 0,         !P.per[2] && kg == P.nz_g - 1};
+    double a[6];
+    double diag = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const double rn = rho[ip + off[q]];
+      const double rlo = (q & 1) ? rc : rn, rhi = (q & 1) ? rn : rc;
+      const double rf = __ddiv_rn(2.0, __dadd_rn(__ddiv_rn(1.0, rlo), __ddiv_rn(1.0, rhi)));
+      a[q] = wall[q] ? 0.0 : __ddiv_rn(__dmul_rn(P.h, P.dt), rf);
+      diag = __dadd_rn(diag, a[q]);
+    }
+    a0[c] = diag;
+    a1[c] = -a[0];
+    a2[c] = -a[1];
+    a3[c] = -a[2];
+    a4[c] = -a[3];
+    a5[c] = -a[4];
+    a6[c] = -a[5];
+    const int64_t fx = i + (int64_t)j * (g.nx + 1) + (int64_t)k * (g.nx + 1) * g.ny;
+    const int64_t fy = i + (int64_t)j * g.nx + (int64_t)k * g.nx * (g.ny + 1);
+    const double dx = __dsub_rn(vx[fx + 1], vx[fx]);
+    const double dy = __dsub_rn(vy[fy + g.nx], vy[fy]);
+    const double dz = __dsub_rn(vz[c + g.cz], vz[c]);
+    double e7 = __dadd_rn(__dadd_rn(dx, dy), dz);
+    if (src) e7 = __dsub_rn(e7, __dmul_rn(src[c], vol));
+    rhs[c] = e7;
+  }
+}
+
 }  // namespace
+
+void launch_assemble_faces(const Geom& g, const DevPtrs& d, double* const* a, double* rhs,
+                           const double* rho_in, const double* vx, const double* vy,
+                           const double* vz, const double* src, double dt, double h, double vol,
+                           int64_t nz_global, int64_t z0, int nx_g, int ny_g, const int* periodic,
+                           cudaStream_t s) {
+  AsmPar P;
+  P.nx_g = nx_g;
+  P.ny_g = ny_g;
+  P.nz_g = nz_global;
+  P.z0 = z0;
+  for (int i = 0; i < 3; ++i) P.per[i] = periodic[i];
+  P.h = h;
+  P.rho_in = P.rho_out = 0.0;
+  P.dt = dt;
+  P.nspheres = 0;
+  k_pad_density<<<148 * 8, 256, 0, s>>>(g, P, rho_in, d.p[1]);
+  k_rows_from_faces<<<148 * 8, 256, 0, s>>>(g, P, d.p[1], vx, vy, vz, src, vol, a[0], a[1], a[2],
+                                            a[3], a[4], a[5], a[6], rhs);
+  cudaMemsetAsync(d.p[1], 0, sizeof(double) * (size_t)g.ptotal, s);
+}
 
 void launch_assemble_spheres(const Geom& g, const DevPtrs& d, double* const* a, double* rhs,
                              const double* spheres, int nspheres, double rho_in, double rho_out,

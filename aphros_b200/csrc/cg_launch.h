@@ -52,4 +52,11 @@ void launch_assemble_spheres(const Geom& g, const DevPtrs& d, double* const* a, 
                              double dt, int64_t nz_global, int64_t z0, int nx_g, int ny_g,
                              const int* periodic, cudaStream_t s);
 
+// general device-side assembly from a cell density and face fluxes (cg_assemble.cu)
+void launch_assemble_faces(const Geom& g, const DevPtrs& d, double* const* a, double* rhs,
+                           const double* rho_in, const double* vx, const double* vy,
+                           const double* vz, const double* src, double dt, double h, double vol,
+                           int64_t nz_global, int64_t z0, int nx_g, int ny_g, const int* periodic,
+                           cudaStream_t s);
+
 }  // namespace acg

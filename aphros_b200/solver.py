@@ -212,6 +212,22 @@ class _CudaSolverBase(Solver):
         capi.check(capi.lib().aphcg_assemble_spheres(self._h, capi.ptr(sph), sph.shape[0],
                                                      rho_in, rho_out, dt))
 
+    def AssembleProjection(self, rho, vx, vy, vz, source=None, dt=1e-3, h=None):
+        """device-side assembly from cell density (with z ghost planes) and face fluxes"""
+        nzl, ny, nx = self.mesh.local_shape
+        arrs = []
+        for a, shp in ((rho, (nzl + 2, ny, nx)), (vx, (nzl, ny, nx + 1)), (vy, (nzl, ny + 1, nx)),
+                       (vz, (nzl + 1, ny, nx))):
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != shp:
+                raise ValueError("expected shape %s, got %s" % (shp, a.shape))
+            arrs.append(a)
+        src = None if source is None else np.ascontiguousarray(source, dtype=np.float64)
+        h = h if h is not None else 1.0 / max(self.mesh.shape)
+        capi.check(capi.lib().aphcg_assemble_projection(
+            self._h, capi.ptr(arrs[0]), capi.ptr(arrs[1]), capi.ptr(arrs[2]), capi.ptr(arrs[3]),
+            capi.ptr(src), dt, h))
+
     def DownloadSystem(self):
         out = np.empty(self.mesh.local_shape + (8,), dtype=np.float64)
         capi.check(capi.lib().aphcg_download_system(self._h, capi.ptr(out), None))

@@ -150,6 +150,20 @@ int aphcg_apply(aphcg_t* h, const double* v, const aphcg_layout* v_layout,
 int aphcg_assemble_spheres(
     aphcg_t* h, const double* spheres, int32_t nspheres, double rho_in,
     double rho_out, double dt);
+/* Device-side assembly of the projection system from what the fluid solver holds
+ * BEFORE it builds rows: what Proj::GetFlux + GetFluxSum compute
+ * (src/solver/proj.ipp:343-383) on a uniform mesh without embedded boundaries, with
+ * wall (zero pressure-gradient coefficient) or periodic domain faces:
+ *   k_f = h*dt/rho_f,  rho_f = harmonic mean of the two cell densities,
+ *   e0 = sum_f k_f,  e[1+q] = -k_f(q),  e7 = sum_q outward(q)*v_f(q) - source*V.
+ * Host arrays of this rank's slab, compact, x fastest:
+ *   rho (nz_local+2, ny, nx): planes -1..nz_local (neighbour slabs' boundary planes);
+ *   vx (nz_local, ny, nx+1), vy (nz_local, ny+1, nx), vz (nz_local+1, ny, nx): volume
+ *   fluxes through the faces;  source (nz_local, ny, nx) or NULL.
+ * 32-40 bytes per cell cross the host link instead of the 64 of assembled rows. */
+int aphcg_assemble_projection(
+    aphcg_t* h, const double* rho, const double* vx, const double* vy, const double* vz,
+    const double* source, double dt, double hcell);
 /* copy the resident system back as rows (for checking the assembler) */
 int aphcg_download_system(aphcg_t* h, double* system, const aphcg_layout* layout);
 
