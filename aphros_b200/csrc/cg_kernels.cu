@@ -192,14 +192,14 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
     const int k = (int)(t / jgroups);
     const int i = (xc * kUT + threadIdx.x) * VX;
     if (i >= g.nx) continue;
-    Vec<VX> ap[UR], rv[UR], dg[UR];
+    Vec<VX> ap[UR], rv[UR], dg[kPre ? UR : 1];
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
       const int j = j0 + u;
       if (j < g.ny) {
         const int64_t idc = i + j * g.cy + k * g.cz;
         ap[u] = ldv_stream<VX>(d.ap + idc);
-        if (kPre) {
+        if constexpr (kPre) {
           rv[u] = ldv_stream<VX>(d.rc + idc);
           dg[u] = ldv_stream<VX>(d.a[0] + idc);
         } else {
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
         for (int v = 0; v < VX; ++v) {
           rv[u].v[v] = fma(-alpha, ap[u].v[v], rv[u].v[v]);  // linear.ipp:89
           amax = fmax(amax, fabs(rv[u].v[v]));               // :91
-          if (kPre) {
+          if constexpr (kPre) {
             zv.v[v] = rv[u].v[v] / dg[u].v[v];
             acc = fma(rv[u].v[v], zv.v[v], acc);             // r.z
             acc2 = fma(rv[u].v[v], rv[u].v[v], acc2);        // r.r
