@@ -193,7 +193,10 @@ def main_ours(args):
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
 
     per_gpu = args.size
-    if args.strong:  # BASELINE config 3: one size^3 domain cut into N z-slabs
+    if args.shape:   # tuning aid: explicit global (nz, ny, nx)
+        shape = tuple(args.shape)
+        nsph, seed = SEEDS[1]
+    elif args.strong:  # BASELINE config 3: one size^3 domain cut into N z-slabs
         shape = (per_gpu, per_gpu, per_gpu)
         nsph, seed = SEEDS[1]
     else:
@@ -346,6 +349,8 @@ def main():
     ap.add_argument("--size", type=int, default=512, help="cells per GPU per direction")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--shape", type=int, nargs=3, default=None, metavar=("NZ", "NY", "NX"),
+                    help="explicit global shape (kernel tuning)")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: one size^3 domain over all GPUs (default: size^3 per GPU)")
     args = ap.parse_args()
