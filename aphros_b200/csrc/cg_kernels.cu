@@ -577,10 +577,13 @@ static dim3 tile_grid(const Geom& g, int vx) {
   return dim3((g.nx + kBX * vx - 1) / (kBX * vx), (g.ny + kBY - 1) / kBY, (g.nzl + kZC - 1) / kZC);
 }
 
+// Upper bound on the CTAs of any kernel that writes per-CTA reduction slots: the tiled
+// kernels (init residual, plain SpMV, Jacobi) and the persistent update kernel, whose
+// grid is capped at 148 SMs x at most 32 CTAs whatever APHCG_UPD_CTAS says.
 unsigned tile_blocks(const Geom& g, int vx) {
-  const dim3 gr = tile_grid(g, vx), gu = update_grid(g, vx);
-  const unsigned a = gr.x * gr.y * gr.z, b = gu.x * gu.y * gu.z;
-  return (a > b ? a : b) + 148 * 32;
+  const dim3 gr = tile_grid(g, vx);
+  const unsigned tiled = gr.x * gr.y * gr.z, persistent = 148u * 32u;
+  return tiled > persistent ? tiled : persistent;
 }
 
 #define APHCG_DISPATCH_VX(vx, ...) \

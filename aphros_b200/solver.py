@@ -20,7 +20,7 @@ missing library or GPU raises, it never falls back to the CPU.
 from __future__ import annotations
 
 import ctypes
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 

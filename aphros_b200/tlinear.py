@@ -81,8 +81,8 @@ def main(argv=None):
         for name, f in (("sol", sol), ("exact", exact), ("diff", diff)):
             f.tofile("%s_0000.raw" % name)
     if args.verbose:
-        if True:
-            sys.stderr.write("linear(%s) '': res=%e iter=%d\n" % (args.solver, info.residual, info.iter))
+        # the report line of linear.ipp:119-124 (m.flags.linreport)
+        sys.stderr.write("linear(%s) '': res=%e iter=%d\n" % (args.solver, info.residual, info.iter))
         print("\nmax_diff_exact=%g" % np.abs(diff).max())
         print("residual=%g" % info.residual)
         print("iter=%d" % info.iter)

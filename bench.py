@@ -50,6 +50,20 @@ def global_shape(n_gpus: int, per_gpu: int):
     return tuple(dims)
 
 
+def measured_traffic(cells, kernel_tag):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
+    (profiles/r01c_traffic.json), if it was taken on this workload; else None."""
+    p = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        if t["cells"] == cells and kernel_tag in t["kernels"]:
+            return t["kernels"][kernel_tag]["k_dir_spmv_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def peak_hbm_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -258,7 +272,8 @@ def main_ours(args):
         ach = B_ALG_DIR_SPMV * cells_local / (ms_dir * 1e-3) / 1e9
         roofline = {
             "bound": "hbm", "kernel": "k_dir_spmv (%s)" % solver.Describe().split(" ")[0], "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": ach / peak, "traffic": None,
+            "frac": ach / peak,
+            "traffic": measured_traffic(cells_local, solver.Describe().split(" ")[0]),
             "algorithmic_bytes_per_launch": B_ALG_DIR_SPMV * cells_local,
             "ms_per_launch": ms_dir, "peak_source": peak_src,
             "update_kernel": {"ms_per_launch": ms_upd,

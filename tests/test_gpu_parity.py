@@ -262,7 +262,6 @@ def test_jacobi(gpu):
 
 
 def test_device_assembly_matches_host_generator(gpu):
-    sys.modules  # noqa
     from aphros_b200 import systems
     n = 48
     sph = systems.random_spheres(16, 5)
@@ -277,8 +276,6 @@ def test_device_assembly_matches_host_generator(gpu):
     scale = np.abs(ref[..., 7]).max()
     assert np.abs(got[..., 7] - ref[..., 7]).max() <= 1e-12 * scale
 
-
-import sys  # noqa: E402
 
 
 def test_nonsymmetric_storage_falls_back(gpu):
