@@ -446,6 +446,11 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
   g.poff = kGhostX + g.py + g.pz;
   g.ptotal = g.pz * (g.nzl + 2);
   h->vx = (g.nx % 2 == 0) ? 2 : 1;
+  // planes per CTA of the tiled kernels: 8 on large meshes; fewer on small ones so that
+  // the grid still fills the 148 SMs several times (they are latency-bound there)
+  g.zc = 8;
+  while (g.zc > 1 && tile_blocks_for(g, h->vx) < 148u * 8u) g.zc /= 2;
+  if (const char* ez = getenv("APHCG_TILE_ZC")) g.zc = std::max(1, atoi(ez));
   h->precond = (ds.flags & APHCG_JACOBI_PRECOND) != 0;
   h->use_graph = !(ds.flags & APHCG_NO_GRAPH);
   if (const char* eg = getenv("APHCG_GRAPH")) h->use_graph = atoi(eg) != 0;

@@ -27,7 +27,6 @@ namespace {
 
 constexpr int kBX = 32;  // threads along x (one warp = one contiguous row segment)
 constexpr int kBY = 8;   // rows per block
-constexpr int kZC = 8;   // planes marched by one block
 
 struct Tile {
   int i, j, k0, k1;
@@ -39,8 +38,8 @@ __device__ __forceinline__ Tile my_tile(const Geom& g) {
   Tile t;
   t.i = (blockIdx.x * kBX + threadIdx.x) * VX;
   t.j = blockIdx.y * kBY + threadIdx.y;
-  t.k0 = blockIdx.z * kZC;
-  t.k1 = min(t.k0 + kZC, g.nzl);
+  t.k0 = blockIdx.z * g.zc;
+  t.k1 = min(t.k0 + g.zc, g.nzl);
   t.active = (t.i < g.nx) && (t.j < g.ny);
   return t;
 }
@@ -574,7 +573,12 @@ __global__ void __launch_bounds__(kBX* kBY) k_jacobi(const Geom g, const DevPtrs
 // launch wrappers
 // ==============================================================================
 static dim3 tile_grid(const Geom& g, int vx) {
-  return dim3((g.nx + kBX * vx - 1) / (kBX * vx), (g.ny + kBY - 1) / kBY, (g.nzl + kZC - 1) / kZC);
+  return dim3((g.nx + kBX * vx - 1) / (kBX * vx), (g.ny + kBY - 1) / kBY, (g.nzl + g.zc - 1) / g.zc);
+}
+
+unsigned tile_blocks_for(const Geom& g, int vx) {
+  const dim3 gr = tile_grid(g, vx);
+  return gr.x * gr.y * gr.z;
 }
 
 // Upper bound on the CTAs of any kernel that writes per-CTA reduction slots: the tiled

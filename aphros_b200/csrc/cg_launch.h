@@ -11,6 +11,8 @@ namespace acg {
 // single: this rank is the only one -- the kernel that finishes a reduction also
 // advances the loop state; otherwise an all-reduce and a k_finish_* follow.
 unsigned tile_blocks(const Geom& g, int vx);
+// CTAs of the tiled kernels for the current g.zc
+unsigned tile_blocks_for(const Geom& g, int vx);
 
 void launch_dir_spmv_plain(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s);
 void launch_update(const Geom& g, const DevPtrs& d, int vx, bool single, bool precond,

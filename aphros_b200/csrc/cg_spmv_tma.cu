@@ -16,6 +16,7 @@
 // registers with 128-bit loads issued a whole step ahead of their use.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 
@@ -426,7 +427,9 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
   int zc = 32;
   const char* env = getenv("APHCG_ZC");
   if (env) zc = atoi(env);
-  while (zc > 4 && (int64_t)tiles * ((g.nzl + zc - 1) / zc) < 148 * 2 * 4) zc /= 2;
+  int zc_min = 4;
+  if (const char* em = getenv("APHCG_ZC_MIN")) zc_min = std::max(1, atoi(em));
+  while (zc > zc_min && (int64_t)tiles * ((g.nzl + zc - 1) / zc) < 148 * 2 * 4) zc /= 2;
   if (zc < 1) zc = 1;
   if (zc > g.nzl) zc = g.nzl;
   p->zc = zc;

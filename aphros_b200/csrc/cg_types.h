@@ -19,6 +19,7 @@ constexpr int kGhostX = 16;
 //   idx = poff + i + j*py + k*pz,  i in [-1,nx], j in [-1,ny], k in [-1,nzl].
 struct Geom {
   int nx, ny, nzl;
+  int zc;               // planes marched by one CTA of the tiled (non-TMA) kernels
   int per_x, per_y;     // periodic in x / y (wrap inside the slab)
   int64_t cy, cz, ncell;
   int64_t py, pz, poff, ptotal;
