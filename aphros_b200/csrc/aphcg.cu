@@ -63,7 +63,15 @@ static_assert(sizeof(IpcBlob) <= APHCG_IPC_BYTES, "blob too large");
 static_assert(sizeof(ncclUniqueId) <= APHCG_UNIQUE_ID_BYTES, "id too large");
 
 constexpr size_t kStageBytes = size_t(128) << 20;
-constexpr int kChunkIters = 16;
+// iterations enqueued (or replayed as one CUDA graph) between two looks at the exit flag
+int ChunkIters() {
+  static int n = [] {
+    const char* e = getenv("APHCG_CHUNK");
+    const int v = e ? atoi(e) : 16;
+    return v >= 1 && v <= 1024 ? v : 16;
+  }();
+  return n;
+}
 
 }  // namespace
 
@@ -221,7 +229,7 @@ int BuildGraph(aphcg_t* h, bool jacobi, cudaGraphExec_t* out) {
   cudaGraph_t graph = nullptr;
   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   int rc = 0;
-  for (int i = 0; i < kChunkIters && rc == 0; ++i) {
+  for (int i = 0; i < ChunkIters() && rc == 0; ++i) {
     rc = jacobi ? EnqueueJacobiIteration(h) : EnqueueIteration(h);
   }
   cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
@@ -360,18 +368,18 @@ int RunLoop(aphcg_t* h, bool jacobi, const aphcg_conf* conf) {
     if (h->use_graph) {
       CK(cudaGraphLaunch(*gx, h->stream));
     } else {
-      for (int i = 0; i < kChunkIters; ++i) {
+      for (int i = 0; i < ChunkIters(); ++i) {
         if (int rc = jacobi ? EnqueueJacobiIteration(h) : EnqueueIteration(h)) return rc;
       }
     }
-    enq += kChunkIters;
+    enq += ChunkIters();
     // poll the exit flag only when it can have fired: always with a tolerance,
     // otherwise once the iteration limit is covered
     if (conf->tol > 0 || enq >= limit) {
       CK(cudaMemcpyAsync(h->h_st, h->st, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
       if (h->h_st->done) break;
-      if (enq > limit + kChunkIters)
+      if (enq > limit + ChunkIters())
         return Fail(APHCG_ERR_STATE, "loop did not terminate (iter=%d)", h->h_st->iter);
     }
   }
@@ -451,6 +459,9 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
   g.zc = 8;
   while (g.zc > 1 && tile_blocks_for(g, h->vx) < 148u * 8u) g.zc /= 2;
   if (const char* ez = getenv("APHCG_TILE_ZC")) g.zc = std::max(1, atoi(ez));
+  // update kernel: as many threads along x as a row has 128-bit pairs (power of two)
+  g.utx = 32;
+  while (g.utx < 256 && g.utx * h->vx < g.nx) g.utx *= 2;
   h->precond = (ds.flags & APHCG_JACOBI_PRECOND) != 0;
   h->use_graph = !(ds.flags & APHCG_NO_GRAPH);
   if (const char* eg = getenv("APHCG_GRAPH")) h->use_graph = atoi(eg) != 0;

@@ -180,16 +180,20 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
   const double alpha = cg_alpha(st);
   double* __restrict__ r = d.r;
   double acc2 = 0.0;
-  const int xchunks = (g.nx + kUT * VX - 1) / (kUT * VX);
-  const int jgroups = (g.ny + UR - 1) / UR;
+  // g.utx threads span one row segment; on narrow meshes (nx/VX < kUT) the remaining
+  // kUT/g.utx thread rows of the CTA take further row groups, so no thread idles
+  const int utx = g.utx, uty = kUT / utx;
+  const int tx = threadIdx.x % utx, ty = threadIdx.x / utx;
+  const int xchunks = (g.nx + utx * VX - 1) / (utx * VX);
+  const int jgroups = (g.ny + UR * uty - 1) / (UR * uty);
   const int64_t nwork = (int64_t)xchunks * jgroups * g.nzl;
   double acc = 0.0, amax = 0.0;
   for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
     const int xc = (int)(w % xchunks);
     const int64_t t = w / xchunks;
-    const int j0 = (int)(t % jgroups) * UR;
+    const int j0 = ((int)(t % jgroups) * uty + ty) * UR;
     const int k = (int)(t / jgroups);
-    const int i = (xc * kUT + threadIdx.x) * VX;
+    const int i = (xc * utx + tx) * VX;
     if (i >= g.nx) continue;
     Vec<VX> ap[UR], rv[UR], dg[kPre ? UR : 1];
 #pragma unroll
@@ -279,8 +283,9 @@ static int update_ctas_per_sm() {
 
 static dim3 update_grid(const Geom& g, int vx) {
   const int ur = update_ur();
-  const int xchunks = (g.nx + kUT * vx - 1) / (kUT * vx);
-  const int64_t nwork = (int64_t)xchunks * ((g.ny + ur - 1) / ur) * g.nzl;
+  const int uty = kUT / g.utx;
+  const int xchunks = (g.nx + g.utx * vx - 1) / (g.utx * vx);
+  const int64_t nwork = (int64_t)xchunks * ((g.ny + ur * uty - 1) / (ur * uty)) * g.nzl;
   const int64_t cap = 148 * (int64_t)update_ctas_per_sm();
   return dim3((unsigned)(nwork < cap ? nwork : cap));
 }

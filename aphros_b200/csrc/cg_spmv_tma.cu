@@ -422,14 +422,20 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
       return fail(msg);
     }
   }
-  // planes per CTA: enough CTAs for a few waves of 2 CTAs/SM, but long columns
+  // Planes per CTA.  Long columns win over many CTAs (each column pays 2 halo planes
+  // and a pipeline fill): measured at 256^3 16 planes x 1024 CTAs beat 8 x 2048
+  // (0.291 vs 0.306 ms), at 128^3 8 x 256 beat 4 x 512 (46 vs 52 us).  So: 32 planes,
+  // halved only while fewer than two waves of 2 CTAs/SM remain, and not below 8
+  // (not below 2 once even that leaves fewer CTAs than SMs).
   const int tiles = ((g.nx + TX - 1) / TX) * ((g.ny + TY - 1) / TY);
   int zc = 32;
   const char* env = getenv("APHCG_ZC");
   if (env) zc = atoi(env);
-  int zc_min = 4;
+  int zc_min = 8;
   if (const char* em = getenv("APHCG_ZC_MIN")) zc_min = std::max(1, atoi(em));
-  while (zc > zc_min && (int64_t)tiles * ((g.nzl + zc - 1) / zc) < 148 * 2 * 4) zc /= 2;
+  auto ctas = [&](int z) { return (int64_t)tiles * ((g.nzl + z - 1) / z); };
+  while (zc > zc_min && ctas(zc) < 148 * 2 * 2) zc /= 2;
+  while (zc > 2 && ctas(zc) < 148) zc /= 2;
   if (zc < 1) zc = 1;
   if (zc > g.nzl) zc = g.nzl;
   p->zc = zc;

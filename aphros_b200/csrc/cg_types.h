@@ -20,6 +20,7 @@ constexpr int kGhostX = 16;
 struct Geom {
   int nx, ny, nzl;
   int zc;               // planes marched by one CTA of the tiled (non-TMA) kernels
+  int utx;              // update kernel: threads along x (power of two, 32..256)
   int per_x, per_y;     // periodic in x / y (wrap inside the slab)
   int64_t cy, cz, ncell;
   int64_t py, pz, poff, ptotal;
