@@ -422,20 +422,27 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
       return fail(msg);
     }
   }
-  // Planes per CTA.  Long columns win over many CTAs (each column pays 2 halo planes
-  // and a pipeline fill): measured at 256^3 16 planes x 1024 CTAs beat 8 x 2048
-  // (0.291 vs 0.306 ms), at 128^3 8 x 256 beat 4 x 512 (46 vs 52 us).  So: 32 planes,
-  // halved only while fewer than two waves of 2 CTAs/SM remain, and not below 8
-  // (not below 2 once even that leaves fewer CTAs than SMs).
+  // Planes per CTA.  A column of z planes costs about z + 4 plane steps (2 halo
+  // planes + pipeline fill) and the chip runs 296 columns at a time (2 CTAs/SM), so
+  // the kernel takes about ceil(ctas/296) * (z + 4) steps: pick the z that minimises
+  // it (ties: the longer column).  Agrees with the measurements: 128^3 8 planes x 256
+  // CTAs beat 4 x 512 (46 vs 52 us), 256^3 16 x 1024 beat 8 x 2048 (0.291 vs 0.306 ms),
+  // 512^3 32 x 4096 = 64 x 2048.
   const int tiles = ((g.nx + TX - 1) / TX) * ((g.ny + TY - 1) / TY);
   int zc = 32;
-  const char* env = getenv("APHCG_ZC");
-  if (env) zc = atoi(env);
-  int zc_min = 8;
-  if (const char* em = getenv("APHCG_ZC_MIN")) zc_min = std::max(1, atoi(em));
-  auto ctas = [&](int z) { return (int64_t)tiles * ((g.nzl + z - 1) / z); };
-  while (zc > zc_min && ctas(zc) < 148 * 2 * 2) zc /= 2;
-  while (zc > 2 && ctas(zc) < 148) zc /= 2;
+  if (const char* env = getenv("APHCG_ZC")) {
+    zc = atoi(env);
+  } else {
+    int64_t best = -1;
+    for (int z = 32; z >= 2; z /= 2) {
+      const int64_t n = (int64_t)tiles * ((g.nzl + z - 1) / z);
+      const int64_t cost = ((n + 295) / 296) * (z + 4);
+      if (best < 0 || cost < best) {
+        best = cost;
+        zc = z;
+      }
+    }
+  }
   if (zc < 1) zc = 1;
   if (zc > g.nzl) zc = g.nzl;
   p->zc = zc;
