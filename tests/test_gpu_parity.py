@@ -402,3 +402,30 @@ def test_device_assembly_from_density_and_fluxes(gpu):
     solver.close()
     assert np.array_equal(got[..., :7], ref[..., :7])
     assert np.array_equal(got[..., 7], ref[..., 7])
+
+
+def test_error_paths(gpu):
+    """call-order and argument errors come back as codes + messages, never as crashes
+    (the adapter turns them into fassert, src/util/logger.h:44-60)"""
+    import ctypes
+    L = capi.lib()
+    solver = SolverConjugateCuda(Conf(tol=1e-6, miniter=0, maxiter=10), {}, Mesh(shape=(8, 8, 8)))
+    info = capi.Info()
+    c = capi.Conf(1e-6, 0, 10)
+    assert L.aphcg_run(solver._h, ctypes.byref(c), ctypes.byref(info)) == -4      # no system yet
+    assert b"no system" in L.aphcg_last_error()
+    with pytest.raises(ValueError):
+        solver.Solve(np.zeros((8, 8, 8, 7)), None, np.zeros((8, 8, 8)))           # wrong row width
+    with pytest.raises(ValueError):
+        solver.Solve(np.zeros((8, 8, 8, 8), dtype=np.float32), None, np.zeros((8, 8, 8)))
+    bad = capi.Layout(0, 4, 64)                                                    # stride_y < nx
+    assert L.aphcg_upload_guess(solver._h, capi.ptr(np.zeros(512)), ctypes.byref(bad)) == -1
+    c_bad = capi.Conf(0.0, 0, -1)
+    s, _ = case_tlinear(8)["system"], None
+    solver.UploadSystem(s)
+    assert L.aphcg_run(solver._h, ctypes.byref(c_bad), ctypes.byref(info)) == -1   # negative maxiter
+    # and the handle is still usable afterwards
+    x = np.zeros((8, 8, 8))
+    assert solver.Solve(s, None, x).iter >= 1
+    solver.close()
+    solver.close()  # idempotent
