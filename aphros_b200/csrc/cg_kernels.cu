@@ -230,10 +230,10 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
         }
         if (kPre) {
           stv_stream<VX>(d.rc + i + j * g.cy + k * g.cz, rv[u]);
-          stv<VX>(r + idp, zv);
+          stv_stream<VX>(r + idp, zv);
           store_images<VX>(g, r, idp, i, j, k, zv, d.r_lo_dst, d.r_hi_dst);
         } else {
-          stv<VX>(r + idp, rv[u]);
+          stv_stream<VX>(r + idp, rv[u]);  // next read is a whole kernel away
           store_images<VX>(g, r, idp, i, j, k, rv[u], d.r_lo_dst, d.r_hi_dst);
         }
       }

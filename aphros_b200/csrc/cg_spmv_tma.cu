@@ -96,7 +96,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
 
 template <int TXT, bool kSingle, bool kSym>
 __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
-    k_dir_spmv_tma(const Geom g, const DevPtrs d, const int zc, const int pd,
+    k_dir_spmv_tma(const Geom g, const DevPtrs d, const int zc, const int pd, const int opts,
                    const __grid_constant__ CUtensorMap map_r,
                    const __grid_constant__ CUtensorMap map_p0,
                    const __grid_constant__ CUtensorMap map_p1) {
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
   double* __restrict__ pn_glob = d.p[par ^ 1];
 
   const int tid = threadIdx.x;
+  const bool pstream = (opts & 1) != 0;  // streaming (evict-first) stores of p_new
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   const int k0 = blockIdx.z * zc;
   const int k1 = min(k0 + zc, g.nzl);
@@ -278,7 +279,11 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
           const bool in1 = (x + 1 >= own_xlo && x + 1 < own_xhi);
           double* dst = pn_glob + g.poff + x + (int64_t)y * g.py + (int64_t)z * g.pz;
           if (in0 && in1) {
-            *reinterpret_cast<double2*>(dst) = o;
+            if (pstream) {
+              __stcs(reinterpret_cast<double2*>(dst), o);  // next read is an iteration away
+            } else {
+              *reinterpret_cast<double2*>(dst) = o;
+            }
           } else if (in0) {
             dst[0] = o.x;
           } else if (in1) {
@@ -370,6 +375,7 @@ struct TmaPlan {
   dim3 grid;
   int zc;
   int pd;  // L2 prefetch distance in planes (0 = off)
+  int opts;  // bit 0: streaming stores of p_new
   int tx;  // tile width in use (64 or 128)
 };
 
@@ -448,6 +454,8 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
   p->zc = zc;
   p->pd = 2;
   if (const char* ep = getenv("APHCG_PREFETCH")) p->pd = atoi(ep);
+  p->opts = 1;  // streaming p_new stores: 1.87 vs 1.90 ms at 512^3
+  if (const char* eo = getenv("APHCG_PSTREAM")) p->opts = atoi(eo) ? 1 : 0;
   p->grid = dim3((g.nx + TX - 1) / TX, (g.ny + TY - 1) / TY, (g.nzl + zc - 1) / zc);
   if (!(TX == 64 ? set_smem_limit<64>() : set_smem_limit<128>())) {
     cudaGetLastError();
@@ -460,8 +468,8 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
 void tma_plan_destroy(TmaPlan* p) { delete p; }
 unsigned tma_plan_blocks(const TmaPlan* p) { return p->grid.x * p->grid.y * p->grid.z; }
 void tma_plan_describe(const TmaPlan* p, char* buf, int buflen) {
-  snprintf(buf, buflen, "tile=%dx%d planes_per_cta=%d stages=%d l2_prefetch=%d ctas=%u", p->tx, TY,
-           p->zc, S, p->pd, tma_plan_blocks(p));
+  snprintf(buf, buflen, "tile=%dx%d planes_per_cta=%d stages=%d l2_prefetch=%d pstream=%d ctas=%u",
+           p->tx, TY, p->zc, S, p->pd, p->opts & 1, tma_plan_blocks(p));
 }
 
 template <int TXT>
@@ -469,7 +477,7 @@ static void launch_cfg(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool s
                        cudaStream_t s) {
   using C = Cfg<TXT>;
 #define APHCG_LAUNCH_TMA(SINGLE, SYM)                                                    \
-  k_dir_spmv_tma<TXT, SINGLE, SYM><<<p->grid, C::NT, C::kSmemBytes, s>>>(g, d, p->zc, p->pd,    \
+  k_dir_spmv_tma<TXT, SINGLE, SYM><<<p->grid, C::NT, C::kSmemBytes, s>>>(g, d, p->zc, p->pd, p->opts, \
                                                                          p->map_r, p->map_p0, p->map_p1)
   if (single) {
     if (sym) APHCG_LAUNCH_TMA(true, true); else APHCG_LAUNCH_TMA(true, false);
