@@ -9,7 +9,7 @@ pressure-Poisson systems (the `linear::Solver<M>` hot path only).
 """
 
 from .solver import (Conf, Info, Mesh, ModuleLinear, Solver, SolverConjugateCuda,  # noqa: F401
-                     SolverJacobiCuda)
+                     SolverConjugateCudaGroup, SolverJacobiCuda, SolverJacobiCudaGroup)
 
 __all__ = ["Conf", "Info", "Mesh", "ModuleLinear", "Solver", "SolverConjugateCuda",
-           "SolverJacobiCuda"]
+           "SolverConjugateCudaGroup", "SolverJacobiCuda", "SolverJacobiCudaGroup"]

@@ -94,6 +94,22 @@ SIGNATURES = {
     "aphcg_comm_init": (ctypes.c_int, [_VP, _VP]),
     "aphcg_ipc_export": (ctypes.c_int, [_VP, _VP]),
     "aphcg_ipc_connect": (ctypes.c_int, [_VP, _VP, ctypes.c_int32]),
+    "aphcg_group_create": (ctypes.c_int, [ctypes.POINTER(_VP), ctypes.POINTER(Desc),
+                                          ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]),
+    "aphcg_group_destroy": (ctypes.c_int, [_VP]),
+    "aphcg_group_size": (ctypes.c_int, [_VP]),
+    "aphcg_group_member": (_VP, [_VP, ctypes.c_int32]),
+    "aphcg_group_slab": (ctypes.c_int, [_VP, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64),
+                                        ctypes.POINTER(ctypes.c_int64)]),
+    "aphcg_group_solve": (ctypes.c_int, [_VP, _VP, _PL, _VP, _PL, _VP, _PL, ctypes.POINTER(Conf),
+                                         ctypes.POINTER(Info)]),
+    "aphcg_group_upload_system": (ctypes.c_int, [_VP, _VP, _PL]),
+    "aphcg_group_upload_guess": (ctypes.c_int, [_VP, _VP, _PL]),
+    "aphcg_group_run": (ctypes.c_int, [_VP, ctypes.POINTER(Conf), ctypes.POINTER(Info)]),
+    "aphcg_group_run_jacobi": (ctypes.c_int, [_VP, ctypes.POINTER(Conf), ctypes.POINTER(Info)]),
+    "aphcg_group_download_solution": (ctypes.c_int, [_VP, _VP, _PL]),
+    "aphcg_group_assemble_spheres": (ctypes.c_int, [_VP, _VP, ctypes.c_int32, ctypes.c_double,
+                                                    ctypes.c_double, ctypes.c_double]),
     "aphcg_timer_start": (ctypes.c_int, [_VP]),
     "aphcg_timer_stop": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_double)]),
     "aphcg_profile_kernels": (ctypes.c_int, [_VP, ctypes.c_int32, ctypes.POINTER(ctypes.c_double),

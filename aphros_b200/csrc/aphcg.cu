@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "cg_group.h"
 #include "cg_launch.h"
 #include "cg_types.h"
 #include "nccl_dl.h"
@@ -58,6 +59,7 @@ struct IpcBlob {  // <= APHCG_IPC_BYTES
   int64_t ptotal, pz, poff, nzl;
   int32_t rank, pid;
   uint64_t base;  // device pointer (valid in the exporting process only)
+  int32_t device, pad;
 };
 static_assert(sizeof(IpcBlob) <= APHCG_IPC_BYTES, "blob too large");
 static_assert(sizeof(ncclUniqueId) <= APHCG_UNIQUE_ID_BYTES, "id too large");
@@ -113,6 +115,7 @@ struct aphcg {
   TmaPlan* tma = nullptr;
   // comm
   ncclComm_t comm = nullptr;
+  GroupSync* gs = nullptr;             // in-process slab group (aphcg_group_*): replaces NCCL
   double* peer[kMaxRanks] = {};        // every rank's slab (own pointer for this rank)
   bool peer_opened[kMaxRanks] = {};
   bool use_mail = true;                // scalar all-reduce through peer mailboxes (else NCCL)
@@ -217,8 +220,10 @@ int EnqueueIteration(aphcg_t* h) {
 int EnqueueJacobiIteration(aphcg_t* h) {
   launch_jacobi(h->g, h->d, h->vx, h->single, h->stream);
   if (!h->single) {
-    if (int rc = AllReduce(h, &h->st->loc_max, ncclMax)) return rc;
-    launch_finish_jacobi(h->d, h->stream);
+    if (!h->use_mail) {
+      if (int rc = AllReduce(h, &h->st->loc_max, ncclMax)) return rc;
+    }
+    launch_finish_jacobi(h->d, h->stream);  // with mailboxes: waits for all ranks' maxima
   }
   return 0;
 }
@@ -248,7 +253,32 @@ int BuildGraph(aphcg_t* h, bool jacobi, cudaGraphExec_t* out) {
 // cross-rank barrier on the stream (orders peer-memory writes before reads)
 int StreamBarrier(aphcg_t* h) {
   if (h->single) return 0;
+  if (h->gs) {  // slabs of one process: drain the stream, then meet the other slab threads
+    CK(cudaStreamSynchronize(h->stream));
+    if (!h->gs->Wait()) return Fail(APHCG_ERR_COMM, "another slab of the group failed");
+    return 0;
+  }
   return AllReduce(h, &h->st->loc_max, ncclMax);
+}
+
+// Sum over ranks of st->loc_sum, once per solve (initial sum r^2), in rank order.
+int AllReduceInitial(aphcg_t* h) {
+  if (!h->gs) return AllReduce(h, &h->st->loc_sum, ncclSum);
+  CK(cudaMemcpyAsync(&h->h_st->loc_sum, &h->st->loc_sum, sizeof(double), cudaMemcpyDeviceToHost,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->gs->red[h->desc.rank] = h->h_st->loc_sum;
+  if (!h->gs->Wait()) return Fail(APHCG_ERR_COMM, "another slab of the group failed");
+  double sum = 0.0;
+  for (int q = 0; q < h->desc.nranks; ++q) sum += h->gs->red[q];
+  // nobody overwrites red[] before every slab has read it
+  if (!h->gs->Wait()) return Fail(APHCG_ERR_COMM, "another slab of the group failed");
+  h->h_st->loc_sum = sum;
+  CK(cudaMemcpyAsync(&h->st->loc_sum, &h->h_st->loc_sum, sizeof(double), cudaMemcpyHostToDevice,
+                     h->stream));
+  // h_st is reused by the loop's polls: the copy must have read it before they land
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 int CheckLayout(const aphcg_t* h, const aphcg_layout* l, aphcg_layout* out) {
@@ -648,7 +678,7 @@ static int CheckRun(aphcg_t* h, const aphcg_conf* conf) {
   if (!h || !conf) return Fail(APHCG_ERR_ARG, "null argument");
   if (!h->have_system) return Fail(APHCG_ERR_STATE, "no system uploaded");
   if (conf->maxiter < 0 || conf->miniter < 0) return Fail(APHCG_ERR_ARG, "negative iteration limit");
-  if (!h->single && (!h->comm || !h->connected))
+  if (!h->single && (!(h->comm || h->gs) || !h->connected))
     return Fail(APHCG_ERR_STATE, "nranks > 1 needs aphcg_comm_init and aphcg_ipc_connect first");
   return 0;
 }
@@ -691,7 +721,7 @@ int aphcg_run(aphcg_t* h, const aphcg_conf* conf, aphcg_info* info) {
   launch_init_residual(h->g, h->d, h->vx, h->single, h->precond, h->stream);
   h->launches++;
   if (!h->single) {
-    if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
+    if (int rc = AllReduceInitial(h)) return rc;
     launch_finish_init(h->d, h->stream);
     h->launches++;
   }
@@ -904,7 +934,7 @@ int aphcg_ipc_export(aphcg_t* h, void* blob_out) {
   if (!h || !blob_out) return Fail(APHCG_ERR_ARG, "null argument");
   if (int rc = SetDevice(h)) return rc;
   IpcBlob b{};
-  CK(cudaIpcGetMemHandle(&b.handle, h->slab));
+  if (!h->gs) CK(cudaIpcGetMemHandle(&b.handle, h->slab));  // in-process groups use plain pointers
   b.ptotal = h->g.ptotal;
   b.pz = h->g.pz;
   b.poff = h->g.poff;
@@ -912,6 +942,7 @@ int aphcg_ipc_export(aphcg_t* h, void* blob_out) {
   b.rank = h->desc.rank;
   b.pid = (int32_t)getpid();
   b.base = (uint64_t)(uintptr_t)h->slab;
+  b.device = h->desc.device;
   memset(blob_out, 0, APHCG_IPC_BYTES);
   memcpy(blob_out, &b, sizeof(b));
   return 0;
@@ -938,6 +969,20 @@ int aphcg_ipc_connect(aphcg_t* h, const void* blobs, int32_t count) {
       h->peer[q] = h->slab;
     } else if (b[q].pid == (int32_t)getpid()) {  // same process: plain peer pointer
       h->peer[q] = (double*)(uintptr_t)b[q].base;
+      if (b[q].device != h->desc.device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, h->desc.device, b[q].device));
+        if (!can)
+          return Fail(APHCG_ERR_COMM, "device %d cannot access device %d's memory (no P2P path)",
+                      h->desc.device, b[q].device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(b[q].device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) {
+          cudaGetLastError();
+        } else if (e != cudaSuccess) {
+          return Fail(APHCG_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", b[q].device,
+                      cudaGetErrorString(e));
+        }
+      }
     } else if (!h->peer[q]) {
       void* ptr = nullptr;
       CK(cudaIpcOpenMemHandle(&ptr, b[q].handle, cudaIpcMemLazyEnablePeerAccess));
@@ -1060,3 +1105,11 @@ int64_t aphcg_launch_count(aphcg_t* h) { return h ? h->launches : 0; }
 int aphcg_launches_per_iter(aphcg_t* h) { return h ? LaunchesPerIter(h) : 0; }
 
 }  // extern "C"
+
+namespace acg {
+void AttachGroupSync(aphcg* h, GroupSync* gs) {
+  h->gs = gs;
+  h->use_mail = true;
+}
+void SetLastError(const char* msg) { g_error = msg ? msg : ""; }
+}  // namespace acg

@@ -514,9 +514,14 @@ __device__ __forceinline__ void jacobi_finish(CgState* st, double* history, doub
   st->iter = it;
   if (it >= st->miniter && (it > st->maxiter || maxdiff < st->tol)) st->done = 1;
 }
-__global__ void k_finish_jacobi(CgState* st, double* history) {
+// Multi-GPU: one warp.  With mailboxes it waits for every rank's max|u_new - u| of this
+// iteration (phase 0); otherwise NCCL has already reduced loc_max.
+__global__ void k_finish_jacobi(const DevPtrs d) {
+  CgState* st = d.st;
   if (st->done) return;
-  jacobi_finish(st, history, st->loc_max);
+  double sum = 0.0, mx = st->loc_max, sum2 = 0.0;
+  if (d.cm.use_mail && !mail_wait(d.cm, st, 0, &sum, &mx, &sum2)) return;
+  if (threadIdx.x == 0) jacobi_finish(st, d.history, mx);
 }
 
 template <int VX, bool kSingle>
@@ -571,6 +576,7 @@ __global__ void __launch_bounds__(kBX* kBY) k_jacobi(const Geom g, const DevPtrs
       st->loc_max = mx;
       if (kSingle) jacobi_finish(st, d.history, mx);
     }
+    if (!kSingle && d.cm.use_mail) mail_push(d.cm, st, 0, 0.0, mx);
   }
 }
 
@@ -649,9 +655,7 @@ void launch_update(const Geom& g, const DevPtrs& d, int vx, bool single, bool pr
 void launch_finish_dir(const DevPtrs& d, cudaStream_t s) { k_finish_dir<<<1, 32, 0, s>>>(d); }
 void launch_finish_upd(const DevPtrs& d, cudaStream_t s) { k_finish_upd<<<1, 32, 0, s>>>(d); }
 void launch_finish_init(const DevPtrs& d, cudaStream_t s) { k_finish_init<<<1, 1, 0, s>>>(d.st); }
-void launch_finish_jacobi(const DevPtrs& d, cudaStream_t s) {
-  k_finish_jacobi<<<1, 1, 0, s>>>(d.st, d.history);
-}
+void launch_finish_jacobi(const DevPtrs& d, cudaStream_t s) { k_finish_jacobi<<<1, 32, 0, s>>>(d); }
 
 void launch_init_residual(const Geom& g, const DevPtrs& d, int vx, bool single, bool precond,
                           cudaStream_t s) {

@@ -22,6 +22,7 @@
 #include <iostream>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "linear/linear.h"
 
@@ -40,8 +41,8 @@ class SolverCuda : public Solver<M> {
   using MIdx = typename M::MIdx;
   enum class Method { conjugate, jacobi };
 
-  SolverCuda(const Conf& conf, Method method, bool maxnorm, int device, unsigned flags,
-             const M& m)
+  SolverCuda(const Conf& conf, Method method, bool maxnorm, int device, int ndevices,
+             int slabs_per_device, unsigned flags, const M& m)
       : Base(conf), method_(method) {
     static_assert(M::dim == 3, "conjugate_cuda: 3-D meshes only");
     static_assert(sizeof(Expr) == 8 * sizeof(double), "row must be 8 doubles");
@@ -62,16 +63,24 @@ class SolverCuda : public Solver<M> {
       fassert(
           ms.GetGlobalSize() == size,
           "conjugate_cuda: one rank must own the whole domain (run aphros with "
-          "px=py=pz=1; the multi-GPU slab path is driven through the C ABI)");
+          "px=py=pz=1 and set cuda_devices to use several GPUs from that rank)");
       for (int i = 0; i < 3; ++i) d.periodic[i] = m.flags.is_periodic[i] ? 1 : 0;
       d.cell_volume = m.GetCellSize().prod();
-      d.device = device;
       d.rank = 0;
       d.nranks = 1;
       d.z0 = 0;
       d.nz_local = size[2];
       d.flags = flags | (maxnorm ? APHCG_MAXNORM : 0);
-      Check(aphcg_create(&s.handle, &d));
+      // the rank-wide index space is cut into `ndevices` z-slabs, one per GPU
+      // device..device+ndevices-1, all driven from this (lead) block
+      // (cuda_slabs_per_device > 1 puts several consecutive slabs on each GPU)
+      fassert(
+          ndevices >= 1 && slabs_per_device >= 1 && ndevices * slabs_per_device <= 16,
+          "conjugate_cuda: cuda_devices x cuda_slabs_per_device must be 1..16");
+      std::vector<int32_t> devices;
+      for (int i = 0; i < ndevices; ++i)
+        for (int k = 0; k < slabs_per_device; ++k) devices.push_back(device + i);
+      Check(aphcg_group_create(&s.group, &d, devices.data(), (int32_t)devices.size()));
       const uint64_t n = uint64_t(size[0]) * size[1] * size[2];
       Check(aphcg_host_alloc(reinterpret_cast<void**>(&s.rows), n * 8 * sizeof(double)));
       Check(aphcg_host_alloc(reinterpret_cast<void**>(&s.x), n * sizeof(double)));
@@ -83,7 +92,7 @@ class SolverCuda : public Solver<M> {
       auto& s = *shared_obj_;
       if (s.rows) aphcg_host_free(s.rows);
       if (s.x) aphcg_host_free(s.x);
-      if (s.handle) aphcg_destroy(s.handle);
+      if (s.group) aphcg_group_destroy(s.group);
     }
   }
 
@@ -117,14 +126,14 @@ class SolverCuda : public Solver<M> {
       aphcg_info info;
       if (method_ == Method::conjugate) {
         // x doubles as guess and solution (fc_init may alias fc_sol, linear.h:40)
-        Check(aphcg_solve(
-            s.handle, s.rows, nullptr, fc_init ? s.x : nullptr, nullptr, s.x, nullptr, &conf,
+        Check(aphcg_group_solve(
+            s.group, s.rows, nullptr, fc_init ? s.x : nullptr, nullptr, s.x, nullptr, &conf,
             &info));
       } else {
-        Check(aphcg_upload_system(s.handle, s.rows, nullptr));
-        Check(aphcg_upload_guess(s.handle, fc_init ? s.x : nullptr, nullptr));
-        Check(aphcg_run_jacobi(s.handle, &conf, &info));
-        Check(aphcg_download_solution(s.handle, s.x, nullptr));
+        Check(aphcg_group_upload_system(s.group, s.rows, nullptr));
+        Check(aphcg_group_upload_guess(s.group, fc_init ? s.x : nullptr, nullptr));
+        Check(aphcg_group_run_jacobi(s.group, &conf, &info));
+        Check(aphcg_group_download_solution(s.group, s.x, nullptr));
       }
       s.info.residual = info.residual;
       s.info.iter = info.iter;
@@ -155,7 +164,7 @@ class SolverCuda : public Solver<M> {
 
  private:
   struct Shared {
-    aphcg_t* handle = nullptr;
+    aphcg_group_t* group = nullptr;  // one slab per GPU; a group of one is the plain solver
     double* rows = nullptr;  // pinned, rank-wide, [nz][ny][nx][8]
     double* x = nullptr;     // pinned, rank-wide, guess in / solution out
     MIdx origin;
@@ -192,7 +201,8 @@ class ModuleLinearConjugateCuda : public ModuleLinear<M> {
     if (var.Int(key("jacobi"), 0)) flags |= APHCG_JACOBI_PRECOND;
     return std::make_unique<SolverCuda<M>>(
         this->GetConf(var, prefix), SolverCuda<M>::Method::conjugate, maxnorm,
-        var.Int("cuda_device", 0), flags, m);
+        var.Int("cuda_device", 0), var.Int("cuda_devices", 1),
+        var.Int("cuda_slabs_per_device", 1), flags, m);
   }
 };
 
@@ -203,7 +213,8 @@ class ModuleLinearJacobiCuda : public ModuleLinear<M> {
   std::unique_ptr<Solver<M>> Make(const Vars& var, std::string prefix, const M& m) override {
     return std::make_unique<SolverCuda<M>>(
         this->GetConf(var, prefix), SolverCuda<M>::Method::jacobi, false,
-        var.Int("cuda_device", 0), 0u, m);
+        var.Int("cuda_device", 0), var.Int("cuda_devices", 1),
+        var.Int("cuda_slabs_per_device", 1), 0u, m);
   }
 };
 

@@ -286,6 +286,156 @@ class SolverJacobiCuda(_CudaSolverBase):
     _method = "jacobi"
 
 
+class _GroupSolverBase(_CudaSolverBase):
+    """The same solver over an in-process slab group (aphcg_group_*, include/aphcg.h):
+    ONE process, ``devices`` = one CUDA ordinal per z-slab; arrays are rank-wide.
+    What the aphros adapter uses when ``cuda_devices`` > 1."""
+
+    def __init__(self, conf: Conf, extra: dict | None, m: Mesh, devices, flags: int = 0):
+        Solver.__init__(self, conf)
+        extra = extra or {}
+        if m.nranks != 1:
+            raise ValueError("a slab group takes the rank-wide mesh (nranks == 1)")
+        self.mesh = m
+        self.devices = [int(d) for d in devices]
+        nz, ny, nx = m.shape
+        d = capi.Desc()
+        d.nx, d.ny, d.nz = nx, ny, nz
+        d.periodic[:] = [int(bool(p)) for p in m.periodic]
+        d.cell_volume = m.cell_volume
+        d.nranks, d.nz_local = 1, nz
+        d.flags = flags | (capi.APHCG_MAXNORM if extra.get("residual_max") else 0)
+        if extra.get("jacobi_precond"):
+            d.flags |= capi.APHCG_JACOBI_PRECOND
+        dev = (ctypes.c_int32 * len(self.devices))(*self.devices)
+        self._g = ctypes.c_void_p()
+        capi.check(capi.lib().aphcg_group_create(ctypes.byref(self._g), ctypes.byref(d), dev,
+                                                 len(self.devices)))
+        self._h = None
+
+    def close(self):
+        if getattr(self, "_g", None) is not None and self._g.value:
+            capi.lib().aphcg_group_destroy(self._g)
+            self._g = ctypes.c_void_p()
+
+    def _member(self, q=0):
+        return ctypes.c_void_p(capi.lib().aphcg_group_member(self._g, q))
+
+    def Slabs(self):
+        out = []
+        for q in range(len(self.devices)):
+            z0, nzl = ctypes.c_int64(), ctypes.c_int64()
+            capi.check(capi.lib().aphcg_group_slab(self._g, q, ctypes.byref(z0), ctypes.byref(nzl)))
+            out.append((z0.value, nzl.value))
+        return out
+
+    def _run(self):
+        info = capi.Info()
+        c = self._conf()
+        L = capi.lib()
+        fn = L.aphcg_group_run if self._method == "conjugate" else L.aphcg_group_run_jacobi
+        capi.check(fn(self._g, ctypes.byref(c), ctypes.byref(info)))
+        return Info(info.residual, info.iter, info.loop_ms, info.total_ms)
+
+    def Solve(self, fc_system, fc_init, fc_sol):
+        L = capi.lib()
+        ls = self.mesh.local_shape
+        self._check_field(fc_system, True)
+        self._check_field(fc_sol, False)
+        lay_s = capi.layout_of(fc_system, ls, 8)
+        lay_x = capi.layout_of(fc_sol, ls)
+        if self._method != "conjugate":
+            self.UploadSystem(fc_system)
+            self._upload_guess(fc_init)
+            info = self._run()
+            self.DownloadSolution(fc_sol)
+            return info
+        info = capi.Info()
+        c = self._conf()
+        if fc_init is not None:
+            self._check_field(fc_init, False)
+            lay_0 = capi.layout_of(fc_init, ls)
+            p0, pl0 = capi.ptr(fc_init), ctypes.byref(lay_0)
+        else:
+            p0, pl0 = None, None
+        capi.check(L.aphcg_group_solve(self._g, capi.ptr(fc_system), ctypes.byref(lay_s), p0, pl0,
+                                       capi.ptr(fc_sol), ctypes.byref(lay_x), ctypes.byref(c),
+                                       ctypes.byref(info)))
+        return Info(info.residual, info.iter, info.loop_ms, info.total_ms)
+
+    def _upload_guess(self, fc_init):
+        if fc_init is None:
+            capi.check(capi.lib().aphcg_group_upload_guess(self._g, None, None))
+        else:
+            self._check_field(fc_init, False)
+            lay = capi.layout_of(fc_init, self.mesh.local_shape)
+            capi.check(capi.lib().aphcg_group_upload_guess(self._g, capi.ptr(fc_init),
+                                                           ctypes.byref(lay)))
+
+    def UploadSystem(self, fc_system):
+        self._check_field(fc_system, True)
+        lay = capi.layout_of(fc_system, self.mesh.local_shape, 8)
+        capi.check(capi.lib().aphcg_group_upload_system(self._g, capi.ptr(fc_system),
+                                                        ctypes.byref(lay)))
+
+    def DownloadSolution(self, fc_sol):
+        self._check_field(fc_sol, False)
+        lay = capi.layout_of(fc_sol, self.mesh.local_shape)
+        capi.check(capi.lib().aphcg_group_download_solution(self._g, capi.ptr(fc_sol),
+                                                            ctypes.byref(lay)))
+        return fc_sol
+
+    def AssembleSpheres(self, spheres, rho_in=1e-3, rho_out=1.0, dt=1e-3):
+        sph = np.ascontiguousarray(spheres, dtype=np.float64).reshape(-1, 4)
+        capi.check(capi.lib().aphcg_group_assemble_spheres(self._g, capi.ptr(sph), sph.shape[0],
+                                                           rho_in, rho_out, dt))
+
+    def History(self, n=None):
+        n = int(n if n is not None else self.conf.maxiter + 2)
+        out = np.zeros(max(n, 1), dtype=np.float64)
+        got = capi.check(capi.lib().aphcg_get_history(self._member(0), capi.ptr(out), n))
+        return out[:got]
+
+    def Describe(self) -> str:
+        buf = ctypes.create_string_buffer(512)
+        capi.check(capi.lib().aphcg_describe(self._member(0), buf, 512))
+        return buf.value.decode() + " slabs=%d" % len(self.devices)
+
+    def LaunchCount(self):
+        return sum(int(capi.lib().aphcg_launch_count(self._member(q)))
+                   for q in range(len(self.devices)))
+
+    def LaunchesPerIter(self):
+        return int(capi.lib().aphcg_launches_per_iter(self._member(0)))
+
+    def TimerStart(self):
+        for q in range(len(self.devices)):
+            capi.check(capi.lib().aphcg_timer_start(self._member(q)))
+
+    def TimerStop(self) -> float:
+        worst = 0.0
+        for q in range(len(self.devices)):
+            ms = ctypes.c_double()
+            capi.check(capi.lib().aphcg_timer_stop(self._member(q), ctypes.byref(ms)))
+            worst = max(worst, ms.value)
+        return worst
+
+    def _unsupported(self, *a, **k):
+        raise NotImplementedError("not available on a slab group; use the slab handles")
+
+    Apply = AssembleProjection = DownloadSystem = ProfileKernels = _unsupported
+    CommInit = IpcExport = IpcConnect = _unsupported
+
+
+class SolverConjugateCudaGroup(_GroupSolverBase):
+    """SolverConjugateCuda over several GPUs of one process."""
+    _method = "conjugate"
+
+
+class SolverJacobiCudaGroup(_GroupSolverBase):
+    _method = "jacobi"
+
+
 class ModuleLinear:
     """linear::ModuleLinear<M> registry (src/linear/linear.h:59-76,
     src/util/module.h:21-85)."""
@@ -335,6 +485,11 @@ class ModuleLinearConjugateCuda(ModuleLinear):
             flags |= capi.APHCG_NO_GRAPH
         if int(var.get("linsolver_" + prefix + "_cuda_tma", 1)) == 0:
             flags |= capi.APHCG_NO_TMA
+        ndev = int(var.get("cuda_devices", 1))
+        if ndev > 1:  # one process, several GPUs: z-slabs on devices cuda_device..+ndev-1
+            first = int(var.get("cuda_device", 0))
+            return SolverConjugateCudaGroup(self.GetConf(var, prefix), extra, m,
+                                            range(first, first + ndev), flags)
         return SolverConjugateCuda(self.GetConf(var, prefix), extra, m, flags)
 
 

@@ -185,6 +185,44 @@ int aphcg_comm_init(aphcg_t* h, const void* id);
 int aphcg_ipc_export(aphcg_t* h, void* blob_out);
 int aphcg_ipc_connect(aphcg_t* h, const void* blobs, int32_t count);
 
+/* ---- in-process slab group: ONE process drives several GPUs ----------------------
+ * For callers that own the whole rank-wide arrays in one address space -- aphros
+ * started without MPI on a multi-GPU node ("single process, G devices,
+ * driven from the lead block of a single aphros rank").  The group cuts the domain of
+ * `desc` (rank, nranks, z0, nz_local and device are ignored) into ndevices contiguous
+ * z-slabs, one per entry of devices[] (sizes differ by at most one plane, larger
+ * slabs first), creates an ordinary handle per slab and wires them with plain peer
+ * pointers (cudaDeviceEnablePeerAccess).  Every group call runs one host thread per
+ * slab; the loop is the multi-GPU loop above (halo planes and scalars through peer
+ * memory, written by the kernels), and NCCL is not used at all: the two collective
+ * steps of a solve are a stream synchronize plus a thread barrier.  A device ordinal
+ * may appear more than once in devices[] (its slabs then share that GPU; meant for
+ * testing the slab path on a single-GPU machine).
+ * Arrays are RANK-WIDE: layouts address global inner cell (i,j,k) as
+ * offset + i + j*stride_y + k*stride_z; NULL = compact (nz, ny, nx).
+ * After any group call fails the group is unusable; destroy it. */
+typedef struct aphcg_group aphcg_group_t;
+int aphcg_group_create(aphcg_group_t** out, const aphcg_desc* desc, const int32_t* devices,
+                       int32_t ndevices);
+int aphcg_group_destroy(aphcg_group_t* g);
+int aphcg_group_size(aphcg_group_t* g);
+/* the handle of one slab (owned by the group), e.g. for aphcg_describe / timers */
+aphcg_t* aphcg_group_member(aphcg_group_t* g, int32_t slab);
+int aphcg_group_slab(aphcg_group_t* g, int32_t slab, int64_t* z0, int64_t* nz_local);
+/* the group forms of aphcg_solve / upload / run / download (same meaning) */
+int aphcg_group_solve(
+    aphcg_group_t* g, const double* system, const aphcg_layout* system_layout,
+    const double* x0, const aphcg_layout* x0_layout, double* x,
+    const aphcg_layout* x_layout, const aphcg_conf* conf, aphcg_info* info);
+int aphcg_group_upload_system(aphcg_group_t* g, const double* system, const aphcg_layout* layout);
+int aphcg_group_upload_guess(aphcg_group_t* g, const double* x0, const aphcg_layout* layout);
+int aphcg_group_run(aphcg_group_t* g, const aphcg_conf* conf, aphcg_info* info);
+int aphcg_group_run_jacobi(aphcg_group_t* g, const aphcg_conf* conf, aphcg_info* info);
+int aphcg_group_download_solution(aphcg_group_t* g, double* x, const aphcg_layout* layout);
+int aphcg_group_assemble_spheres(
+    aphcg_group_t* g, const double* spheres, int32_t nspheres, double rho_in, double rho_out,
+    double dt);
+
 /* Device-side timing on the handle's stream (CUDA events): start records an
  * event; stop records another, waits for it and returns the milliseconds between. */
 int aphcg_timer_start(aphcg_t* h);

@@ -4,6 +4,10 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Slab-group tests put several slabs on ONE GPU; a slab's one-warp reduction kernel spins
+# on its peers' mailboxes, so the peers' streams must not share a hardware queue with it
+# (read by the CUDA driver at initialisation; inherited by the subprocesses tests start).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

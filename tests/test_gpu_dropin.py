@@ -41,6 +41,27 @@ def test_module_selected_by_name_matches_conjugate(gpu, block, backend):
     assert rel_max_abs(xg, xr) <= 1e-10
 
 
+@pytest.mark.parametrize("solver", ["conjugate", "jacobi"])
+def test_module_over_several_slabs(gpu, solver):
+    """`cuda_devices` / `cuda_slabs_per_device`: the lead block drives an in-process slab
+    group (aphcg_group_*); same answer as the reference's own module.  Two slabs on one
+    GPU run everywhere; with >= 2 GPUs the slabs also go to separate devices."""
+    cpu = _need()
+    from aphros_b200 import capi
+    s, _ = systems.tlinear_system(32)
+    tol = 1e-9 if solver == "conjugate" else 1e-4
+    kw = dict(tol=tol, maxiter=3000, block=16)
+    xr, itr, resr, _ = cpu.solve_reference(s, solver=solver, **kw)
+    extras = ["set int cuda_slabs_per_device 2"]
+    if capi.device_count() >= 2:
+        extras.append("set int cuda_devices 2")
+    for extra in extras:
+        xg, itg, resg, _ = cpu.solve_reference(s, solver=solver + "_cuda", plugin=PLUGIN,
+                                               extra=extra, **kw)
+        assert abs(itg - itr) <= 2, (extra, itg, itr)
+        assert rel_max_abs(xg, xr) <= (1e-10 if solver == "conjugate" else 1e-9), extra
+
+
 def test_guess_nonperiodic_and_maxnorm(gpu):
     cpu = _need()
     s, _ = systems.density_poisson_system(32, nspheres=6, seed=4, rho_in=0.05)

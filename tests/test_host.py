@@ -52,6 +52,23 @@ def test_fails_loudly_without_gpu(built):
         SolverConjugateCuda(Conf(), {}, Mesh(shape=(8, 8, 8)))
 
 
+def test_group_argument_checks_and_partition(built):
+    """aphcg_group_*: argument checks run before any CUDA call; without a GPU creation
+    fails loudly; the slab rule is distr.slab_partition's"""
+    from aphros_b200 import SolverConjugateCudaGroup
+    with pytest.raises(capi.AphcgError, match="cannot cut"):
+        SolverConjugateCudaGroup(Conf(), {}, Mesh(shape=(3, 8, 8)), [0, 0, 0, 0])
+    with pytest.raises(capi.AphcgError, match="1..16 slabs"):
+        SolverConjugateCudaGroup(Conf(), {}, Mesh(shape=(64, 8, 8)), [0] * 17)
+    if capi.lib().aphcg_device_count() == 0:
+        with pytest.raises(capi.AphcgError, match="no CUDA device"):
+            SolverConjugateCudaGroup(Conf(), {}, Mesh(shape=(8, 8, 8)), [0, 1])
+    mod = ModuleLinear.GetInstance("conjugate_cuda")
+    var = {"hypre_symm_tol": 1e-3, "hypre_symm_maxiter": 10, "cuda_devices": 20}
+    with pytest.raises(capi.AphcgError, match="1..16 slabs"):
+        mod.Make(var, "symm", Mesh(shape=(64, 8, 8)))
+
+
 def test_argument_checks(built):
     L = capi.lib()
     h = ctypes.c_void_p()
