@@ -56,7 +56,7 @@ class Conf(ctypes.Structure):
 class Info(ctypes.Structure):
     _fields_ = [("residual", ctypes.c_double), ("iter", ctypes.c_int32),
                 ("reserved", ctypes.c_int32), ("loop_ms", ctypes.c_double),
-                ("total_ms", ctypes.c_double)]
+                ("total_ms", ctypes.c_double), ("residual0", ctypes.c_double)]
 
 
 _lib = None

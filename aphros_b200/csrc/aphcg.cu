@@ -10,6 +10,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstddef>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -261,21 +263,33 @@ int StreamBarrier(aphcg_t* h) {
   return AllReduce(h, &h->st->loc_max, ncclMax);
 }
 
-// Sum over ranks of st->loc_sum, once per solve (initial sum r^2), in rank order.
+// Sums over ranks of st->loc_sum and st->loc_sum2, once per solve (the numerator of the
+// first alpha and sum r^2 of the initial residual), in rank order.
 int AllReduceInitial(aphcg_t* h) {
-  if (!h->gs) return AllReduce(h, &h->st->loc_sum, ncclSum);
-  CK(cudaMemcpyAsync(&h->h_st->loc_sum, &h->st->loc_sum, sizeof(double), cudaMemcpyDeviceToHost,
-                     h->stream));
+  if (!h->gs) {
+    if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
+    return AllReduce(h, &h->st->loc_sum2, ncclSum);
+  }
+  static_assert(offsetof(CgState, loc_sum2) - offsetof(CgState, loc_sum) == 2 * sizeof(double),
+                "loc_sum, loc_max, loc_sum2 are copied as one block");
+  CK(cudaMemcpyAsync(&h->h_st->loc_sum, &h->st->loc_sum, 3 * sizeof(double),
+                     cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  h->gs->red[h->desc.rank] = h->h_st->loc_sum;
+  const int me = h->desc.rank, n = h->desc.nranks;
+  h->gs->red[me] = h->h_st->loc_sum;
+  h->gs->red2[me] = h->h_st->loc_sum2;
   if (!h->gs->Wait()) return Fail(APHCG_ERR_COMM, "another slab of the group failed");
-  double sum = 0.0;
-  for (int q = 0; q < h->desc.nranks; ++q) sum += h->gs->red[q];
+  double sum = 0.0, sum2 = 0.0;
+  for (int q = 0; q < n; ++q) {
+    sum += h->gs->red[q];
+    sum2 += h->gs->red2[q];
+  }
   // nobody overwrites red[] before every slab has read it
   if (!h->gs->Wait()) return Fail(APHCG_ERR_COMM, "another slab of the group failed");
   h->h_st->loc_sum = sum;
-  CK(cudaMemcpyAsync(&h->st->loc_sum, &h->h_st->loc_sum, sizeof(double), cudaMemcpyHostToDevice,
-                     h->stream));
+  h->h_st->loc_sum2 = sum2;
+  CK(cudaMemcpyAsync(&h->st->loc_sum, &h->h_st->loc_sum, 3 * sizeof(double),
+                     cudaMemcpyHostToDevice, h->stream));
   // h_st is reused by the loop's polls: the copy must have read it before they land
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -697,6 +711,7 @@ static int FinishRun(aphcg_t* h, aphcg_info* info) {
     info->residual = h->h_st->residual;
     info->iter = h->h_st->iter;
     info->reserved = 0;
+    info->residual0 = sqrt(h->h_st->rnorm2_0 / h->desc.cell_volume);
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]));
     info->loop_ms = ms;

@@ -43,6 +43,7 @@ class GroupSync {
   int size() const { return n_; }
   // scratch of the host-side scalar all-reduce (one value per slab, summed in slab order)
   double red[kMaxRanks] = {};
+  double red2[kMaxRanks] = {};
 
  private:
   std::mutex mu_;

@@ -322,7 +322,10 @@ __global__ void k_finish_upd(const DevPtrs d) {
   if (d.cm.use_mail && !mail_wait(d.cm, st, 1, &sum, &mx, &sum2)) return;
   if (threadIdx.x == 0) cg_finish_upd(st, d.history, sum, mx, st->precond ? sum2 : sum);
 }
-__global__ void k_finish_init(CgState* st) { st->rr = st->loc_sum; }
+__global__ void k_finish_init(CgState* st) {
+  st->rr = st->loc_sum;
+  st->rnorm2_0 = st->loc_sum2;
+}
 
 // ------------------------------------------------------------------------------
 // k_residual: out = sign*(A f [+ rhs]) from a padded field f (stage "init",
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(kBX* kBY)
   __shared__ int sm_flag;
   CgState* st = d.st;
   const Tile t = my_tile<VX>(g);
-  double acc = 0.0;
+  double acc = 0.0, acc2 = 0.0;  // acc2: sum r^2 when acc is sum r.z (preconditioned start)
   if (t.active) {
     for (int k = t.k0; k < t.k1; ++k) {
       const int64_t idc = t.i + t.j * g.cy + k * g.cz;
@@ -374,6 +377,7 @@ __global__ void __launch_bounds__(kBX* kBY)
         for (int v = 0; v < VX; ++v) {
           zv.v[v] = res.v[v] / a[0].v[v];
           acc = fma(res.v[v], zv.v[v], acc);
+          acc2 = fma(res.v[v], res.v[v], acc2);
         }
         stv<VX>(d.rc + idc, res);
         stv<VX>(out + idp, zv);
@@ -389,13 +393,22 @@ __global__ void __launch_bounds__(kBX* kBY)
   if (!kInit) return;
   if (d.r_lo_dst != nullptr || d.r_hi_dst != nullptr) __threadfence_system();
   const double bsum = block_reduce<false>(acc, sm);
+  const double bsum2 = kPre ? block_reduce<false>(acc2, sm) : bsum;
   const int tid = threadIdx.x + blockDim.x * threadIdx.y;
-  if (tid == 0) d.partials[block_id()] = bsum;
+  if (tid == 0) {
+    d.partials[block_id()] = bsum;
+    if (kPre) d.partials3[block_id()] = bsum2;
+  }
   if (last_block(&st->counter_a, num_blocks(), &sm_flag)) {
     const double tot = reduce_slots<false>(d.partials, num_blocks(), sm);
+    const double tot2 = kPre ? reduce_slots<false>(d.partials3, num_blocks(), sm) : tot;
     if (tid == 0) {
       st->loc_sum = tot;
-      if (kSingle) st->rr = tot;
+      st->loc_sum2 = tot2;
+      if (kSingle) {
+        st->rr = tot;
+        st->rnorm2_0 = tot2;
+      }
     }
   }
 }

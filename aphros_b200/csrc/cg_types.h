@@ -58,6 +58,7 @@ struct CgState {
   double rr;        // current                            (dot_r / next dot_r_prev)
   double rr_prev;   // before the last update             (dot_r_prev)
   double rnorm2;    // sum r^2 (the residual norm; equals rr without preconditioner)
+  double rnorm2_0;  // sum r^2 of the initial residual (reported as aphcg_info.residual0)
   double pAp;       // sum p*Ap                           (dot_p_lp)
   double max_r;     // max |r|
   double alpha_prev;  // alpha of the last completed iteration (x update is deferred

@@ -42,6 +42,7 @@ class Info:
     iter: int = 0
     loop_ms: float = 0.0
     total_ms: float = 0.0
+    residual0: float = 0.0  # norm of the initial residual (CG runs)
 
 
 @dataclass
@@ -134,7 +135,7 @@ class _CudaSolverBase(Solver):
         c = self._conf()
         fn = capi.lib().aphcg_run if self._method == "conjugate" else capi.lib().aphcg_run_jacobi
         capi.check(fn(self._h, ctypes.byref(c), ctypes.byref(info)))
-        return Info(info.residual, info.iter, info.loop_ms, info.total_ms)
+        return Info(info.residual, info.iter, info.loop_ms, info.total_ms, info.residual0)
 
     # -- linear::Solver<M>::Solve ---------------------------------------------------
     def Solve(self, fc_system, fc_init, fc_sol):
@@ -165,7 +166,7 @@ class _CudaSolverBase(Solver):
         capi.check(L.aphcg_solve(self._h, capi.ptr(fc_system), ctypes.byref(lay_s), p0, pl0,
                                  capi.ptr(fc_sol), ctypes.byref(lay_x), ctypes.byref(c),
                                  ctypes.byref(info)))
-        return Info(info.residual, info.iter, info.loop_ms, info.total_ms)
+        return Info(info.residual, info.iter, info.loop_ms, info.total_ms, info.residual0)
 
     # -- device-resident pieces (bench, tests) ----------------------------------------
     def _upload_guess(self, fc_init):
@@ -335,7 +336,7 @@ class _GroupSolverBase(_CudaSolverBase):
         L = capi.lib()
         fn = L.aphcg_group_run if self._method == "conjugate" else L.aphcg_group_run_jacobi
         capi.check(fn(self._g, ctypes.byref(c), ctypes.byref(info)))
-        return Info(info.residual, info.iter, info.loop_ms, info.total_ms)
+        return Info(info.residual, info.iter, info.loop_ms, info.total_ms, info.residual0)
 
     def Solve(self, fc_system, fc_init, fc_sol):
         L = capi.lib()
@@ -361,7 +362,7 @@ class _GroupSolverBase(_CudaSolverBase):
         capi.check(L.aphcg_group_solve(self._g, capi.ptr(fc_system), ctypes.byref(lay_s), p0, pl0,
                                        capi.ptr(fc_sol), ctypes.byref(lay_x), ctypes.byref(c),
                                        ctypes.byref(info)))
-        return Info(info.residual, info.iter, info.loop_ms, info.total_ms)
+        return Info(info.residual, info.iter, info.loop_ms, info.total_ms, info.residual0)
 
     def _upload_guess(self, fc_init):
         if fc_init is None:

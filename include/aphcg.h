@@ -99,6 +99,10 @@ typedef struct {
   int32_t reserved;
   double loop_ms;      /* device time of the CG loop alone (CUDA events) */
   double total_ms;     /* device time of everything the call enqueued */
+  double residual0;    /* sqrt(sum r0^2 / V) of the initial residual r0 = -(A x0 + e7)
+                          (linear.ipp:48-56): lets a caller express a relative
+                          tolerance, which the reference's Conf cannot; 0 after
+                          aphcg_run_jacobi, which forms no residual */
 } aphcg_info;
 
 const char* aphcg_last_error(void);

@@ -429,3 +429,28 @@ def test_error_paths(gpu):
     assert solver.Solve(s, None, x).iter >= 1
     solver.close()
     solver.close()  # idempotent
+
+
+@pytest.mark.parametrize("precond", [False, True])
+def test_initial_residual_norm_is_reported(gpu, precond):
+    """aphcg_info.residual0 = sqrt(sum r0^2 / V), r0 = -(A x0 + e7) (linear.ipp:48-56): what a
+    caller needs to turn a relative tolerance into the reference's absolute one"""
+    from cases import initial_residual
+    from aphros_b200 import SolverConjugateCudaGroup
+    case = case_density(24, rho_in=0.1)
+    shape = case["system"].shape[:3]
+    x0 = random_guess(shape)
+    want = initial_residual(case["system"], x0, case["periodic"])
+    m = Mesh(shape=shape, periodic=case["periodic"])
+    conf = Conf(tol=0.0, miniter=0, maxiter=3)
+    for make in (lambda: SolverConjugateCuda(conf, {"jacobi_precond": precond}, m),
+                 lambda: SolverConjugateCudaGroup(conf, {"jacobi_precond": precond}, m, [0, 0, 0])):
+        solver = make()
+        info = solver.Solve(case["system"], x0, np.zeros(shape))
+        solver.close()
+        assert abs(info.residual0 - want) <= 1e-12 * want
+    want0 = rhs_norm_of(case)
+    solver = SolverConjugateCuda(conf, {"jacobi_precond": precond}, m)
+    info = solver.Solve(case["system"], None, np.zeros(shape))
+    solver.close()
+    assert abs(info.residual0 - want0) <= 1e-12 * want0
