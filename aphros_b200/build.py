@@ -68,7 +68,8 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.run([nvcc, "-shared", "-o", LIB] + objs + ["-ldl", "-cudart", "static"], check=True)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs
+                   + ["-ldl", "-cudart", "static"], check=True)
     return LIB
 
 

@@ -98,6 +98,7 @@ struct aphcg {
   unsigned nslots = 0;
   int hist_cap = 0;
   double* stage[2] = {};
+  size_t stage_bytes = 0;
   cudaEvent_t stage_free[2] = {}, stage_ready[2] = {};
   cudaEvent_t ev[4] = {};
   DevPtrs d{};
@@ -360,10 +361,13 @@ int SystemResident(aphcg_t* h) {
   return 0;
 }
 
+// Two staging buffers for the row upload: 128 MB each, or one xy-plane of rows if that is
+// larger (the transpose works on whole planes).
 int EnsureStage(aphcg_t* h) {
+  h->stage_bytes = std::max(kStageBytes, (size_t)h->g.cz * 64);
   for (int b = 0; b < 2; ++b) {
     if (!h->stage[b]) {
-      CK(cudaMalloc(&h->stage[b], kStageBytes));
+      CK(cudaMalloc(&h->stage[b], h->stage_bytes));
       CK(cudaEventCreateWithFlags(&h->stage_free[b], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->stage_ready[b], cudaEventDisableTiming));
     }
@@ -622,8 +626,7 @@ int aphcg_upload_system(aphcg_t* h, const double* system, const aphcg_layout* la
   if (int rc = EnsureStage(h)) return rc;
   const Geom& g = h->g;
   const size_t plane = (size_t)g.cz * 64;
-  const int per_chunk = (int)std::max<size_t>(1, kStageBytes / plane);
-  if (plane > kStageBytes) return Fail(APHCG_ERR_ARG, "xy-plane larger than the staging buffer");
+  const int per_chunk = (int)std::max<size_t>(1, h->stage_bytes / plane);
   int b = 0;
   for (int k0 = 0; k0 < g.nzl; k0 += per_chunk, b ^= 1) {
     const int nk = std::min(per_chunk, g.nzl - k0);

@@ -188,6 +188,74 @@ def main_reference(args):
 # ---------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------
+def main_group(args):
+    """The same step driven by ONE process over N GPUs through the in-process slab group
+    (aphcg_group_*: what the aphros adapter uses for `cuda_devices N`).  Comparison record for
+    the process-per-GPU launch the driver uses; prints its own JSON line ("mode": "group")."""
+    from aphros_b200 import Conf, Mesh, SolverConjugateCudaGroup, capi, systems
+
+    n = args.gpus
+    if capi.device_count() < n:
+        raise SystemExit("--group --gpus %d needs %d CUDA devices" % (n, n))
+    shape = (args.size,) * 3 if args.strong else global_shape(n, args.size)
+    nsph, seed = SEEDS[1] if args.strong else SEEDS.get(n, (512 * n, 20240610 + n))
+    nsph = max(1, int(nsph * (args.size / 512.0) ** 3))
+    cells = int(np.prod(shape))
+    solver = SolverConjugateCudaGroup(Conf(tol=0.0, miniter=0, maxiter=MAXITER), {},
+                                      Mesh(shape=shape, periodic=(False, False, False)), range(n))
+    solver.AssembleSpheres(systems.random_spheres(nsph, seed))
+
+    def step():
+        solver.UploadGuess(None)
+        return solver.Run()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = solver.LaunchCount()
+    solver.TimerStart()
+    iters, loop_ms = 0, 0.0
+    for _ in range(args.steps):
+        info = step()
+        iters += info.iter
+        loop_ms += info.loop_ms
+    dev_ms = solver.TimerStop()
+    clocks = sampler.stop()
+    line = {
+        "mode": "group", "metric": METRIC, "value": cells * iters / (dev_ms * 1e-3), "unit": UNIT,
+        "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "%dx%dx%d (nz,ny,nx), %d spheres 1000:1, Neumann walls, one process "
+                               "driving %d z-slabs (aphcg_group_*), 101 iterations per step"
+                               % (shape + (nsph, n)),
+                   "cells": cells, "kernels": solver.Describe()},
+        "loop_ms_per_step": loop_ms / args.steps,
+        "gpu_launches": int(solver.LaunchCount() - launches0), "clocks": clocks,
+    }
+    if not args.no_e2e and cells * 88 < 48e9:
+        rows = capi.PinnedArray(shape + (8,))
+        x0 = capi.PinnedArray(shape)
+        xs = capi.PinnedArray(shape)
+        for q, (z0, nzl) in enumerate(solver.Slabs()):
+            capi.check(capi.lib().aphcg_download_system(solver._member(q),
+                                                        capi.ptr(rows.array[z0:z0 + nzl]), None))
+        x0.array[...] = 0.0
+        solver.Solve(rows.array, x0.array, xs.array)
+        t0 = time.perf_counter()
+        k = max(1, min(args.steps, 3))
+        it2 = sum(solver.Solve(rows.array, x0.array, xs.array).iter for _ in range(k))
+        sec = time.perf_counter() - t0
+        line["e2e"] = {"value": cells * it2 / sec, "unit": UNIT, "h2d_bytes_per_step": cells * 72,
+                       "d2h_bytes_per_step": cells * 8, "steps": k, "ms_per_step": sec * 1e3 / k,
+                       "api": "aphcg_group_solve (C ABI), rank-wide pinned host arrays"}
+        rows.free(), x0.free(), xs.free()
+    print(json.dumps(line))
+    solver.close()
+    return 0
+
+
 def main_converge(args, solver, shape, nsph, world, rank, dist):
     """BASELINE config 4 ("CG to 1e-8 relative residual"): ONE solve of the resident system
     from a zero guess to residual < reltol * initial residual.  The reference's Conf only has
@@ -413,6 +481,9 @@ def main():
                     help="explicit global shape (kernel tuning)")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: one size^3 domain over all GPUs (default: size^3 per GPU)")
+    ap.add_argument("--group", action="store_true",
+                    help="one process drives all --gpus devices (in-process slab group) instead of "
+                         "one process per GPU")
     ap.add_argument("--converge", type=float, default=0.0, metavar="RELTOL",
                     help="instead of the bench step: one solve to RELTOL x initial residual")
     ap.add_argument("--maxiter", type=int, default=100000, help="iteration limit of --converge")
@@ -423,6 +494,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)
+    if args.group:
+        return main_group(args)
     return main_ours(args)
 
 
