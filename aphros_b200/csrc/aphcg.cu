@@ -109,6 +109,7 @@ struct aphcg {
   cudaGraphExec_t gexec_jacobi = nullptr;
   bool use_graph = true;
   bool use_tma = false;
+  bool xbatch = true;     // batched deferred x updates in the TMA kernel (CgState::xbatch)
   bool precond = false;   // opt-in Jacobi-preconditioned recurrence (APHCG_JACOBI_PRECOND)
   double* rc = nullptr;   // compact residual, preconditioned mode only
   double* partials3 = nullptr;
@@ -385,6 +386,7 @@ int WriteState(aphcg_t* h, const aphcg_conf* conf) {
   s.cell_volume = h->desc.cell_volume;
   s.hist_cap = h->hist_cap;
   s.seq_base = (++h->runs) << 32;
+  s.xbatch = (h->use_tma && h->xbatch) ? 1 : 0;
   *h->h_st = s;
   CK(cudaMemcpyAsync(h->st, h->h_st, sizeof(CgState), cudaMemcpyHostToDevice, h->stream));
   return 0;
@@ -549,6 +551,7 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
   h->use_mail = !(ds.flags & APHCG_NCCL_REDUCE);
   if (const char* em = getenv("APHCG_ALLREDUCE")) h->use_mail = strcmp(em, "nccl") != 0;
   if (const char* es = getenv("APHCG_SYM")) h->allow_sym = atoi(es) != 0;
+  if (const char* ex = getenv("APHCG_XBATCH")) h->xbatch = atoi(ex) != 0;
   const char* env = getenv("APHCG_SPMV");
   bool want_tma = !(ds.flags & APHCG_NO_TMA);
   if (env && !strcmp(env, "plain")) want_tma = false;
@@ -1085,21 +1088,26 @@ int aphcg_profile_kernels(aphcg_t* h, int32_t iters, double* ms_dir_spmv, double
   }
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
-  double sd = 0, su = 0;
+  double sd = 0, su = 0, sd_par[2] = {0, 0};
+  int n_par[2] = {0, 0};
   for (int i = 0; i < iters; ++i) {
     float a = 0, b = 0;
     CK(cudaEventElapsedTime(&a, ev[3 * i], ev[3 * i + 1]));
     CK(cudaEventElapsedTime(&b, ev[3 * i + 1], ev[3 * i + 2]));
     sd += a;
     su += b;
+    sd_par[i & 1] += a;
+    n_par[i & 1]++;
   }
   *ms_dir_spmv = sd / iters;
   *ms_update = su / iters;
   if (getenv("APHCG_VERBOSE")) {
     float tot = 0;
     cudaEventElapsedTime(&tot, ev[0], ev[3 * (size_t)iters - 1]);
-    fprintf(stderr, "aphcg profile: %d iterations, dir %.4f ms + upd %.4f ms = %.4f; span/iter %.4f ms\n",
-            iters, sd / iters, su / iters, (sd + su) / iters, tot / iters);
+    fprintf(stderr, "aphcg profile: %d iterations, dir %.4f ms (even %.4f, odd %.4f) + upd %.4f ms = %.4f; "
+            "span/iter %.4f ms\n",
+            iters, sd / iters, sd_par[0] / std::max(n_par[0], 1), sd_par[1] / std::max(n_par[1], 1),
+            su / iters, (sd + su) / iters, tot / iters);
   }
   for (auto& e : ev) cudaEventDestroy(e);
   h->launches += 1 + 2 * (int64_t)iters;

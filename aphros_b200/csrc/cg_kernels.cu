@@ -452,12 +452,16 @@ __global__ void k_gather_field(const Geom g, const double* __restrict__ u, doubl
   }
 }
 
-// x += alpha_prev * p : the deferred x update of the last iteration ("iter2", linear.ipp:88)
+// x += alpha_prev * p : the deferred x update of the last iteration ("iter2", linear.ipp:88).
+// With batched updates (CgState::xbatch) an even number of completed iterations leaves the
+// last TWO updates pending; they are applied in iteration order.
 template <int VX>
 __global__ void __launch_bounds__(kBX* kBY) k_final_update(const Geom g, const DevPtrs d) {
   const CgState* st = d.st;
-  const double alpha_prev = st->alpha_prev;
+  const double alpha_prev = st->alpha_prev, alpha_prev2 = st->alpha_prev2;
   const double* __restrict__ p = d.p[st->iter & 1];
+  const double* __restrict__ p2 = d.p[(st->iter & 1) ^ 1];
+  const bool two = st->xbatch && st->iter >= 2 && (st->iter & 1) == 0;
   const Tile t = my_tile<VX>(g);
   if (!t.active) return;
   for (int k = t.k0; k < t.k1; ++k) {
@@ -465,6 +469,11 @@ __global__ void __launch_bounds__(kBX* kBY) k_final_update(const Geom g, const D
     const int64_t idp = g.poff + t.i + t.j * g.py + k * g.pz;
     const Vec<VX> pv = ldv<VX>(p + idp);
     Vec<VX> uu = ldv<VX>(d.u + idc);
+    if (two) {
+      const Vec<VX> pv2 = ldv<VX>(p2 + idp);
+#pragma unroll
+      for (int v = 0; v < VX; ++v) uu.v[v] = fma(alpha_prev2, pv2.v[v], uu.v[v]);
+    }
 #pragma unroll
     for (int v = 0; v < VX; ++v) uu.v[v] = fma(alpha_prev, pv.v[v], uu.v[v]);
     stv<VX>(d.u + idc, uu);

@@ -182,6 +182,7 @@ __device__ __forceinline__ void cg_finish_dir(CgState* st, double pap) { st->pAp
 // rnorm2: sum r^2, the residual norm.
 __device__ __forceinline__ void cg_finish_upd(CgState* st, double* history, double rr_new,
                                               double max_r, double rnorm2) {
+  st->alpha_prev2 = st->alpha_prev;
   st->alpha_prev = cg_alpha(st);
   st->rr_prev = st->rr;
   st->rr = rr_new;

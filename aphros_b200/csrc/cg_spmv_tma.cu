@@ -115,10 +115,14 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
   CgState* st = d.st;
   if (st->done) return;
   const double beta = cg_beta(st);
-  const double alpha_prev = st->alpha_prev;
+  const double alpha_prev = st->alpha_prev, alpha_prev2 = st->alpha_prev2;
   const int par = st->iter & 1;
   const CUtensorMap* map_po = par ? &map_p1 : &map_p0;
-  double* __restrict__ pn_glob = d.p[par ^ 1];
+  // p_new goes where p_{k-2} lives; the batched x update reads it from there first
+  double* pn_glob = d.p[par ^ 1];
+  // deferred x updates applied by this launch (CgState::xbatch): 1 = the last one (every
+  // iteration), 2 = the last two (even iterations), 0 = none (odd iterations; iteration 0)
+  const int xmode = !st->xbatch ? 1 : ((par || st->iter == 0) ? 0 : 2);
 
   const int tid = threadIdx.x;
   const bool pstream = (opts & 1) != 0;  // streaming (evict-first) stores of p_new
@@ -166,6 +170,8 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
   double acc = 0.0;
   Vec<2> zcarry[2];
   zcarry[0].v[0] = zcarry[0].v[1] = zcarry[1].v[0] = zcarry[1].v[1] = 0.0;
+  Vec<2> p2n[2];
+  p2n[0] = p2n[1] = zcarry[0];
   for (int n = 0; n < np; ++n) {
     const int z = k0 - 1 + n;  // plane whose p_new is formed in this step
     const int m = z - 1;       // plane whose stencil is evaluated in this step
@@ -181,12 +187,15 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
         const int w = min(TX, g.nx - x0);
         // stencil plane of step n+pd is m+pd; x plane is z+pd
         const int pl = (arr == NARR - 1) ? z + pd : m + pd;
-        const bool ok = jj < g.ny && ((arr == NARR - 1) ? (pl >= k0 && pl < k1)
+        const bool ok = jj < g.ny && ((arr == NARR - 1) ? (xmode != 0 && pl >= k0 && pl < k1)
                                                         : (pl >= k0 && pl < k1 + (kSym ? 1 : 0) && pl < g.nzl));
         if (ok) {
           const double* basep;
           if (arr == NARR - 1) {
             basep = d.u;
+            if (xmode == 2 && pl + 1 < k1)  // p_{k-2} of the same cells (loaded one step early)
+              prefetch_l2(pn_glob + g.poff + x0 + (int64_t)jj * g.py + (int64_t)(pl + 1) * g.pz,
+                          (unsigned)w * 8u);
           } else if (kSym) {
             basep = d.a[arr == 0 ? 0 : 2 * arr - 1];  // a0, a1 (x-), a3 (y-), a5 (z-)
           } else {
@@ -251,8 +260,18 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (z_inner && act[h]) {
+      if (z_inner && xmode != 0 && act[h]) {
         uu[h] = ldv_stream<2>(d.u + ci + cj[h] * g.cy + (int64_t)z * g.cz);
+      }
+    }
+    // p_{k-2} of plane z+1, consumed in the NEXT step: the __syncthreads that ends this step
+    // orders the load before any thread of the CTA overwrites those cells with p_new(z+1)
+    Vec<2> p2c[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      p2c[h] = p2n[h];
+      if (xmode == 2 && z + 1 >= k0 && z + 1 < k1 && act[h]) {
+        p2n[h] = ldv_stream<2>(pn_glob + g.poff + ci + (int64_t)cj[h] * g.py + (int64_t)(z + 1) * g.pz);
       }
     }
 
@@ -293,12 +312,16 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
       }
     }
     // -- (b) deferred x update (linear.ipp:88) with p_old of the own cells -------------
-    if (z_inner) {
+    if (z_inner && xmode != 0) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (act[h]) {
           const int o = (2 * ly + h + 1) * BW + 2 + 2 * lx;
           const double2 pv = *reinterpret_cast<const double2*>(sp + o);
+          if (xmode == 2) {  // the older update first: same FMAs, same order as one per iteration
+            uu[h].v[0] = fma(alpha_prev2, p2c[h].v[0], uu[h].v[0]);
+            uu[h].v[1] = fma(alpha_prev2, p2c[h].v[1], uu[h].v[1]);
+          }
           uu[h].v[0] = fma(alpha_prev, pv.x, uu[h].v[0]);
           uu[h].v[1] = fma(alpha_prev, pv.y, uu[h].v[1]);
           stv_stream<2>(d.u + ci + cj[h] * g.cy + (int64_t)z * g.cz, uu[h]);

@@ -63,6 +63,7 @@ struct CgState {
   double max_r;     // max |r|
   double alpha_prev;  // alpha of the last completed iteration (x update is deferred
                       // into the next direction kernel)
+  double alpha_prev2; // alpha of the iteration before that (batched x update, see xbatch)
   double residual;
   // this rank's partial results, all-reduced in place when nranks > 1
   double loc_sum;
@@ -78,6 +79,11 @@ struct CgState {
   int hist_cap;
   unsigned counter_a, counter_b;  // last-block-done tickets
   int error;     // 1: a peer's contribution did not arrive in time (multi-GPU)
+  int xbatch;    // 1: the direction kernel applies the deferred x updates two at a time,
+                 // on even iterations only:  x = fma(a_{k-1}, p_{k-1}, fma(a_{k-2}, p_{k-2}, x))
+                 // -- the same FMAs in the same order as one per iteration, so x is bitwise
+                 // unchanged, but x is read and written every other iteration (p_{k-2} is
+                 // still in the buffer p_k is about to overwrite): 12 instead of 16 B/cell
   unsigned long long seq_base;  // distinguishes the mailbox traffic of successive runs
 };
 

@@ -454,3 +454,21 @@ def test_initial_residual_norm_is_reported(gpu, precond):
     info = solver.Solve(case["system"], None, np.zeros(shape))
     solver.close()
     assert abs(info.residual0 - want0) <= 1e-12 * want0
+
+
+def test_batched_x_update_is_bitwise_the_per_iteration_update(gpu, monkeypatch):
+    """The TMA kernel applies the deferred `x += alpha p` (linear.ipp:88) two iterations at a
+    time, in iteration order with the same FMAs; APHCG_XBATCH=0 applies one per iteration.
+    Same bits for odd and even iteration counts, with and without an initial guess."""
+    case = case_density(32, rho_in=0.01)
+    shape = case["system"].shape[:3]
+    x0 = random_guess(shape)
+    for maxiter in (0, 1, 2, 37, 60):
+        out = []
+        for xb in ("1", "0"):
+            monkeypatch.setenv("APHCG_XBATCH", xb)
+            for guess in (None, x0):
+                x, info, _ = gpu_solve(case, Conf(tol=0.0, miniter=0, maxiter=maxiter), x0=guess)
+                assert info.iter == maxiter + 1
+                out.append(x)
+        assert np.array_equal(out[0], out[2]) and np.array_equal(out[1], out[3]), maxiter
