@@ -52,8 +52,8 @@ def global_shape(n_gpus: int, per_gpu: int):
 
 def measured_traffic(cells, kernel_tag):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture
-    (profiles/r01c_traffic.json), if it was taken on this workload; else None."""
-    p = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    (profiles/r01d_traffic.json), if it was taken on this workload; else None."""
+    p = os.path.join(ROOT, "profiles", "r01d_traffic.json")
     try:
         with open(p) as f:
             t = json.load(f)
