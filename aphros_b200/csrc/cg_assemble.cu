@@ -198,10 +198,11 @@ void launch_assemble_faces(const Geom& g, const DevPtrs& d, double* const* a, do
   P.rho_in = P.rho_out = 0.0;
   P.dt = dt;
   P.nspheres = 0;
-  k_pad_density<<<148 * 8, 256, 0, s>>>(g, P, rho_in, d.p[1]);
-  k_rows_from_faces<<<148 * 8, 256, 0, s>>>(g, P, d.p[1], vx, vy, vz, src, vol, a[0], a[1], a[2],
+  // scratch: the padded residual field (see launch_assemble_spheres)
+  k_pad_density<<<148 * 8, 256, 0, s>>>(g, P, rho_in, d.r);
+  k_rows_from_faces<<<148 * 8, 256, 0, s>>>(g, P, d.r, vx, vy, vz, src, vol, a[0], a[1], a[2],
                                             a[3], a[4], a[5], a[6], rhs);
-  cudaMemsetAsync(d.p[1], 0, sizeof(double) * (size_t)g.ptotal, s);
+  cudaMemsetAsync(d.r, 0, sizeof(double) * (size_t)g.ptotal, s);
 }
 
 void launch_assemble_spheres(const Geom& g, const DevPtrs& d, double* const* a, double* rhs,
@@ -220,13 +221,17 @@ void launch_assemble_spheres(const Geom& g, const DevPtrs& d, double* const* a, 
   P.rho_out = rho_out;
   P.dt = dt;
   P.nspheres = nspheres;
-  // density goes through p[1] (free between solves); its ghost layers are
-  // restored to zero afterwards because the solver relies on zero ghosts at
-  // non-periodic boundaries.
-  k_density<<<148 * 8, 256, 0, s>>>(g, P, spheres, d.p[1]);
-  k_rows_from_density<<<148 * 8, 256, 0, s>>>(g, P, d.p[1], a[0], a[1], a[2], a[3], a[4], a[5],
+  // The density goes through the padded residual field r, free between solves; its ghost
+  // layers are restored to zero afterwards because the solver relies on finite ghosts at
+  // non-periodic boundaries.  NOT through p[1]: a neighbour rank's aphcg_upload_guess stores
+  // its guess planes into this rank's p[1] ghost planes whenever it gets there -- it does not
+  // wait for this rank -- and a zero landing between the two kernels below would be read as
+  // a zero density (infinite coefficients).  Ghost planes of r are only written by peers
+  // inside a run, which every rank enters through a barrier.
+  k_density<<<148 * 8, 256, 0, s>>>(g, P, spheres, d.r);
+  k_rows_from_density<<<148 * 8, 256, 0, s>>>(g, P, d.r, a[0], a[1], a[2], a[3], a[4], a[5],
                                               a[6], rhs);
-  cudaMemsetAsync(d.p[1], 0, sizeof(double) * (size_t)g.ptotal, s);
+  cudaMemsetAsync(d.r, 0, sizeof(double) * (size_t)g.ptotal, s);
 }
 
 }  // namespace acg

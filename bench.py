@@ -222,8 +222,10 @@ def main_group(args):
         loop_ms += info.loop_ms
     dev_ms = solver.TimerStop()
     clocks = sampler.stop()
+    if not (np.isfinite(info.residual) and np.isfinite(info.residual0) and info.residual0 > 0):
+        raise SystemExit("bench: non-finite residual (%r, initial %r)" % (info.residual, info.residual0))
     line = {
-        "mode": "group", "metric": METRIC, "value": cells * iters / (dev_ms * 1e-3), "unit": UNIT,
+        "mode": "group", "residual": {"initial": info.residual0, "after_step": info.residual}, "metric": METRIC, "value": cells * iters / (dev_ms * 1e-3), "unit": UNIT,
         "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "dtype": "f64",
         "data": "synthetic",
@@ -267,6 +269,8 @@ def main_converge(args, solver, shape, nsph, world, rank, dist):
     solver.SetConf(Conf(tol=0.0, miniter=0, maxiter=0))
     solver.UploadGuess(None)
     res0 = solver.Run().residual0
+    if not (np.isfinite(res0) and res0 > 0):
+        raise SystemExit("bench --converge: initial residual is %r" % res0)
     solver.SetConf(Conf(tol=args.converge * res0, miniter=0, maxiter=args.maxiter))
     solver.UploadGuess(None)
     if world > 1:
@@ -366,6 +370,9 @@ def main_ours(args):
         iters += info.iter
         loop_ms += info.loop_ms
     dev_ms = solver.TimerStop()
+    if not (np.isfinite(info.residual) and np.isfinite(info.residual0) and info.residual0 > 0):
+        raise SystemExit("bench: non-finite residual (%r, initial %r): the step did not compute"
+                         % (info.residual, info.residual0))
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
@@ -454,6 +461,7 @@ def main_ours(args):
             "loop_ms_per_step": loop_ms / args.steps,
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "residual": {"initial": info.residual0, "after_step": info.residual},
         }
         if roofline:
             line["roofline"] = roofline

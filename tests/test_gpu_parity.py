@@ -180,7 +180,8 @@ def test_maxnorm(gpu):
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 2), (3, 5, 7), (5, 9, 130), (2, 8, 128), (9, 16, 258),
-                                   (33, 8, 64), (1, 40, 40)])
+                                   (33, 8, 64), (1, 40, 40), (2, 8, 1024), (3, 10, 1100),
+                                   (2, 1030, 64), (70, 8, 640)])
 def test_ragged_shapes(gpu, shape):
     """odd nx (scalar path), partial tiles, single plane (2-D), tiny meshes"""
     s, exact = __import__("aphros_b200").systems.tlinear_system(None, shape=shape)
@@ -472,3 +473,19 @@ def test_batched_x_update_is_bitwise_the_per_iteration_update(gpu, monkeypatch):
                 assert info.iter == maxiter + 1
                 out.append(x)
         assert np.array_equal(out[0], out[2]) and np.array_equal(out[1], out[3]), maxiter
+
+
+@pytest.mark.parametrize("shape", [(4, 16, 1024), (4, 1024, 128), (132, 8, 516)])
+def test_wide_meshes_with_walls(gpu, shape):
+    """rows / planes wider than one CTA's reach of every kernel (nx = 1024 is the x extent of
+    the 8-GPU weak-scaling domain), Neumann walls, variable density, against the oracle.
+    Six iterations only: these thin bars are so ill-conditioned that after 21 iterations a
+    1e-16 relative perturbation of the right-hand side moves the reference's own x by 8e-5
+    (and its block size by 6e-5); after six the reference is reproducible to 1e-13."""
+    case = case_density(None, nspheres=5, seed=11, rho_in=0.1, shape=shape)
+    conf = Conf(tol=0.0, miniter=0, maxiter=5)
+    x, info, hist = gpu_solve(case, conf)
+    xo, it_o, res_o, hist_o = oracle_solve(case, tol=0.0, miniter=0, maxiter=5)
+    assert info.iter == it_o == 6
+    np.testing.assert_allclose(hist, hist_o, rtol=1e-9)
+    assert rel_max_abs(x, xo) <= X_TOL
