@@ -69,6 +69,15 @@ def test_group_argument_checks_and_partition(built):
         mod.Make(var, "symm", Mesh(shape=(64, 8, 8)))
 
 
+def test_group_sync_barrier(tmp_path):
+    """the thread barrier / host all-reduce of the in-process slab group (cg_group.h)"""
+    exe = str(tmp_path / "group_sync_test")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-pthread", "-I" + os.path.join(ROOT, "aphros_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "cpp", "group_sync_test.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_argument_checks(built):
     L = capi.lib()
     h = ctypes.c_void_p()
