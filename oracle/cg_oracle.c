@@ -303,6 +303,8 @@ int cg_oracle_jacobi(const cg_oracle_desc* d, const double* sys,
   geom_t g = make_geom(d);
   double* u = padded_from_compact(&g, x0);
   double* un = (double*)calloc((size_t)g.ntot, sizeof(double));
+  double* const buf0 = u;  /* u and un swap every iteration; free the allocations by name */
+  double* const buf1 = un;
   if (!u || !un) {
     free(u); free(un);
     return -1;
@@ -342,6 +344,7 @@ int cg_oracle_jacobi(const cg_oracle_desc* d, const double* sys,
   compact_from_padded(&g, u, x);
   *residual = res;
   *iter_out = iter;
-  free(u); free(un);
+  free(buf0);
+  free(buf1);
   return 0;
 }
