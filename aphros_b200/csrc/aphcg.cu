@@ -507,7 +507,7 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
   // planes per CTA of the tiled kernels: 8 on large meshes; fewer on small ones so that
   // the grid still fills the 148 SMs several times (they are latency-bound there)
   g.zc = 8;
-  while (g.zc > 1 && tile_blocks_for(g, h->vx) < 148u * 8u) g.zc /= 2;
+  while (g.zc > 1 && tile_blocks_for(g, h->vx) < (unsigned)kNumSMs * 8u) g.zc /= 2;
   if (const char* ez = getenv("APHCG_TILE_ZC")) g.zc = std::max(1, atoi(ez));
   // update kernel: as many threads along x as a row has 128-bit pairs (power of two)
   g.utx = 32;

@@ -199,8 +199,8 @@ void launch_assemble_faces(const Geom& g, const DevPtrs& d, double* const* a, do
   P.dt = dt;
   P.nspheres = 0;
   // scratch: the padded residual field (see launch_assemble_spheres)
-  k_pad_density<<<148 * 8, 256, 0, s>>>(g, P, rho_in, d.r);
-  k_rows_from_faces<<<148 * 8, 256, 0, s>>>(g, P, d.r, vx, vy, vz, src, vol, a[0], a[1], a[2],
+  k_pad_density<<<kNumSMs * 8, 256, 0, s>>>(g, P, rho_in, d.r);
+  k_rows_from_faces<<<kNumSMs * 8, 256, 0, s>>>(g, P, d.r, vx, vy, vz, src, vol, a[0], a[1], a[2],
                                             a[3], a[4], a[5], a[6], rhs);
   cudaMemsetAsync(d.r, 0, sizeof(double) * (size_t)g.ptotal, s);
 }
@@ -228,8 +228,8 @@ void launch_assemble_spheres(const Geom& g, const DevPtrs& d, double* const* a, 
   // wait for this rank -- and a zero landing between the two kernels below would be read as
   // a zero density (infinite coefficients).  Ghost planes of r are only written by peers
   // inside a run, which every rank enters through a barrier.
-  k_density<<<148 * 8, 256, 0, s>>>(g, P, spheres, d.r);
-  k_rows_from_density<<<148 * 8, 256, 0, s>>>(g, P, d.r, a[0], a[1], a[2], a[3], a[4], a[5],
+  k_density<<<kNumSMs * 8, 256, 0, s>>>(g, P, spheres, d.r);
+  k_rows_from_density<<<kNumSMs * 8, 256, 0, s>>>(g, P, d.r, a[0], a[1], a[2], a[3], a[4], a[5],
                                               a[6], rhs);
   cudaMemsetAsync(d.r, 0, sizeof(double) * (size_t)g.ptotal, s);
 }

@@ -286,7 +286,7 @@ static dim3 update_grid(const Geom& g, int vx) {
   const int uty = kUT / g.utx;
   const int xchunks = (g.nx + g.utx * vx - 1) / (g.utx * vx);
   const int64_t nwork = (int64_t)xchunks * ((g.ny + ur * uty - 1) / (ur * uty)) * g.nzl;
-  const int64_t cap = 148 * (int64_t)update_ctas_per_sm();
+  const int64_t cap = kNumSMs * (int64_t)update_ctas_per_sm();
   return dim3((unsigned)(nwork < cap ? nwork : cap));
 }
 
@@ -619,7 +619,7 @@ unsigned tile_blocks_for(const Geom& g, int vx) {
 // grid is capped at 148 SMs x at most 32 CTAs whatever APHCG_UPD_CTAS says.
 unsigned tile_blocks(const Geom& g, int vx) {
   const dim3 gr = tile_grid(g, vx);
-  const unsigned tiled = gr.x * gr.y * gr.z, persistent = 148u * 32u;
+  const unsigned tiled = gr.x * gr.y * gr.z, persistent = (unsigned)kNumSMs * 32u;
   return tiled > persistent ? tiled : persistent;
 }
 
@@ -645,7 +645,7 @@ void launch_dir_spmv_plain(const Geom& g, const DevPtrs& d, int vx, bool single,
 }
 
 void launch_check_symmetry(const Geom& g, const DevPtrs& d, int* flag, cudaStream_t s) {
-  k_check_symmetry<<<148 * 8, 256, 0, s>>>(g, d, flag);
+  k_check_symmetry<<<kNumSMs * 8, 256, 0, s>>>(g, d, flag);
 }
 
 template <int VX, int UR, bool kPre>
@@ -712,7 +712,7 @@ void launch_scatter_field(const Geom& g, const double* src, int64_t off, int64_t
 
 void launch_gather_field(const Geom& g, const double* u, double* dst, int64_t off, int64_t sy,
                          int64_t sz, cudaStream_t s) {
-  k_gather_field<<<148 * 8, 256, 0, s>>>(g, u, dst, off, sy, sz);
+  k_gather_field<<<kNumSMs * 8, 256, 0, s>>>(g, u, dst, off, sy, sz);
 }
 
 void launch_final_update(const Geom& g, const DevPtrs& d, int vx, cudaStream_t s) {
@@ -722,12 +722,12 @@ void launch_final_update(const Geom& g, const DevPtrs& d, int vx, cudaStream_t s
 
 void launch_rows_to_soa(const Geom& g, const double* rows, int64_t off, int64_t sy, int64_t sz,
                         int k0, int nk, double* const* a, double* rhs, cudaStream_t s) {
-  k_rows_to_soa<<<148 * 16, 256, 0, s>>>(g, rows, off, sy, sz, k0, nk, a[0], a[1], a[2], a[3],
+  k_rows_to_soa<<<kNumSMs * 16, 256, 0, s>>>(g, rows, off, sy, sz, k0, nk, a[0], a[1], a[2], a[3],
                                          a[4], a[5], a[6], rhs);
 }
 
 void launch_soa_to_rows(const Geom& g, const DevPtrs& d, double* rows, cudaStream_t s) {
-  k_soa_to_rows<<<148 * 8, 256, 0, s>>>(g, d, rows);
+  k_soa_to_rows<<<kNumSMs * 8, 256, 0, s>>>(g, d, rows);
 }
 
 void launch_jacobi(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s) {

@@ -465,7 +465,8 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
     int64_t best = -1;
     for (int z = 32; z >= 2; z /= 2) {
       const int64_t n = (int64_t)tiles * ((g.nzl + z - 1) / z);
-      const int64_t cost = ((n + 295) / 296) * (z + 4);
+      const int64_t slots = 2 * kNumSMs;  // resident CTAs of this kernel (2 per SM)
+      const int64_t cost = ((n + slots - 1) / slots) * (z + 4);
       if (best < 0 || cost < best) {
         best = cost;
         zc = z;

@@ -5,6 +5,10 @@
 
 namespace acg {
 
+// Streaming multiprocessors of the one target, B200 (sm_100a): grids of the grid-stride and
+// persistent kernels are sized in multiples of it.
+constexpr int kNumSMs = 148;
+
 // Ghost offset of inner cell i=0 inside a padded row: keeps inner rows 128-byte
 // aligned so that pair (128-bit) accesses and TMA boxes start on line boundaries.
 constexpr int kGhostX = 16;
