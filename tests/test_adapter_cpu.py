@@ -1,0 +1,133 @@
+"""CPU test of the aphros adapter's HOST logic (aphros_b200/plugin/linear_conjugate_cuda.cpp).
+
+The reference's own classes (oracle/_ref/ref_cg: DistrSolver, MeshCartesian, stage coroutines,
+the ModuleLinear factory) load the adapter and select `conjugate_cuda` by name, exactly as in
+tests/test_gpu_dropin.py -- but the C ABI underneath is answered by a TEST DOUBLE
+(tests/cpp/fake_aphcg.c, preloaded in front of libaphcg.so) that forwards to the CPU oracle and
+logs every call.  What is checked here is what the adapter does around the C ABI: gather of the
+blocks' rows into rank-wide arrays, scatter of the solution and its halo exchange, the geometry,
+periodicity, cell volume, flags, Conf and device list it passes.  The product has no CPU path;
+the arithmetic of the CUDA library is tested by the `-m gpu` tests."""
+
+from __future__ import annotations
+
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from aphros_b200 import systems
+from cases import rel_max_abs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PLUGIN = os.path.join(ROOT, "aphros_b200", "plugin", "libaphcg_aphros.so")
+
+
+@pytest.fixture(scope="module")
+def fake(built, tmp_path_factory):
+    from oracle import cpu
+    if not (cpu.have_reference() and os.path.exists(PLUGIN)):
+        pytest.skip("prebuilt oracle/_ref and adapter not present")
+    d = tmp_path_factory.mktemp("fake")
+    so = str(d / "libfake_aphcg.so")
+    subprocess.run(["gcc", "-O2", "-fPIC", "-std=gnu99", "-ffp-contract=off", "-fno-fast-math", "-shared",
+                    "-o", so, os.path.join(ROOT, "tests", "cpp", "fake_aphcg.c"),
+                    os.path.join(ROOT, "oracle", "cg_oracle.c"), "-lm"], check=True)
+    return so
+
+
+def run(fake, tmp_path, system, x0=None, solver="conjugate_cuda", **kw):
+    """(x, iter, residual, log lines) of one ref_cg run with the adapter over the test double"""
+    from oracle import cpu
+    log = str(tmp_path / ("log_%d.txt" % len(os.listdir(tmp_path))))
+    env = {"LD_PRELOAD": fake, "FAKE_APHCG_LOG": log}
+    x, it, res, _ = cpu.solve_reference(system, x0, solver=solver, plugin=PLUGIN, env=env, **kw)
+    with open(log) as f:
+        lines = f.read().splitlines()
+    return x, it, res, lines
+
+
+@pytest.mark.parametrize("backend", ["native", "local"])
+@pytest.mark.parametrize("block,threads", [(16, 1), (8, 4), (32, 1)])
+def test_gather_scatter_over_blocks(fake, tmp_path, backend, block, threads):
+    """8 / 64 / 1 blocks per rank, serial and OpenMP over blocks: the rank-wide system the
+    adapter assembles is the reference's, so the answer is `conjugate`'s"""
+    from oracle import cpu
+    s, _ = systems.tlinear_system(32)
+    kw = dict(tol=1e-9, maxiter=2000, block=block, threads=threads,
+              extra="set string backend %s" % backend)
+    xr, itr, resr, _ = cpu.solve_reference(s, solver="conjugate", **kw)
+    xg, itg, resg, log = run(fake, tmp_path, s, **kw)
+    assert abs(itg - itr) <= 2 and resg < 1e-9
+    assert rel_max_abs(xg, xr) <= 1e-10
+    create = [l for l in log if l.startswith("create")]
+    assert len(create) == 1, "one device object per rank, owned by the lead block"
+    m = re.match(r"create nx=32 ny=32 nz=32 periodic=111 volume=(\S+) flags=0 devices=\[0\]", create[0])
+    assert m, create[0]
+    assert abs(float(m.group(1)) - cpu.reference_cell_volume((32, 32, 32), block)) < 1e-20
+    assert sum(l.startswith("solve") for l in log) == 1 and log[-1] == "destroy"
+    # (the driver always passes an fc_init field, zero when no guess is given)
+    assert "tol=1.0000000000000001e-09 miniter=0 maxiter=2000" in [l for l in log if l.startswith("solve")][0]
+
+
+def test_guess_walls_maxnorm_and_ragged_mesh(fake, tmp_path):
+    """non-cubic mesh, Neumann walls (periodic flags 000), an initial guess (fc_init != nullptr),
+    `linsolver_symm_maxnorm` -> APHCG_MAXNORM"""
+    from oracle import cpu
+    shape = (16, 24, 32)
+    s, _ = systems.density_poisson_system(None, nspheres=4, seed=3, rho_in=0.2, shape=shape)
+    x0 = np.random.default_rng(5).standard_normal(shape) * 1e-3
+    kw = dict(periodic=(False, False, False), tol=0.0, maxiter=25, block=8, maxnorm=True)
+    xr, itr, resr, _ = cpu.solve_reference(s, x0, solver="conjugate", **kw)
+    xg, itg, resg, log = run(fake, tmp_path, s, x0, **kw)
+    assert itg == itr == 26
+    # the test double sums in one-block order, the reference per 8^3 block: rounding-level
+    # differences, amplified by the 5:1 density jump over 26 non-converged iterations
+    assert abs(resg - resr) <= 1e-7 * resr
+    assert rel_max_abs(xg, xr) <= 1e-7
+    create = [l for l in log if l.startswith("create")][0]
+    assert "nx=32 ny=24 nz=16 periodic=000" in create and "flags=1 " in create
+    assert "solve guess=1" in "\n".join(log)
+
+
+def test_config_keys_reach_the_c_abi(fake, tmp_path):
+    """cuda_device / cuda_devices / cuda_slabs_per_device -> device list; linsolver_symm_cuda_graph,
+    _cuda_tma, _jacobi -> flags (APHCG_NO_GRAPH=2, APHCG_NO_TMA=4, APHCG_JACOBI_PRECOND=32)"""
+    s, _ = systems.tlinear_system(16)
+    kw = dict(tol=1e-3, maxiter=50, block=8)
+    cases = [("set int cuda_device 2\nset int cuda_devices 3", "devices=[2,3,4]", "flags=0 "),
+             ("set int cuda_slabs_per_device 2", "devices=[0,0]", "flags=0 "),
+             ("set int cuda_devices 2\nset int cuda_slabs_per_device 2", "devices=[0,0,1,1]", "flags=0 "),
+             ("set int linsolver_symm_cuda_graph 0", "devices=[0]", "flags=2 "),
+             ("set int linsolver_symm_cuda_tma 0\nset int linsolver_symm_jacobi 1", "devices=[0]", "flags=36 ")]
+    for extra, dev, flags in cases:
+        _, _, _, log = run(fake, tmp_path, s, extra=extra, **kw)
+        create = [l for l in log if l.startswith("create")][0]
+        assert dev in create and flags in create, (extra, create)
+    with pytest.raises(RuntimeError, match="cuda_devices x cuda_slabs_per_device must be 1..16"):
+        run(fake, tmp_path, s, extra="set int cuda_devices 17", **kw)
+
+
+def test_jacobi_module_calls(fake, tmp_path):
+    """jacobi_cuda: upload_system, upload_guess, run_jacobi, download_solution, same answer as
+    the reference's `jacobi`"""
+    from oracle import cpu
+    s, _ = systems.tlinear_system(16)
+    kw = dict(tol=1e-4, maxiter=2000, block=8)
+    xr, itr, resr, _ = cpu.solve_reference(s, solver="jacobi", **kw)
+    xg, itg, resg, log = run(fake, tmp_path, s, solver="jacobi_cuda", **kw)
+    assert itg == itr and rel_max_abs(xg, xr) <= 1e-12
+    calls = [l.split()[0] for l in log]
+    assert calls == ["create", "upload_system", "upload_guess", "run_jacobi", "download_solution",
+                     "destroy"], calls
+
+
+def test_repeated_solves_reuse_the_device_object(fake, tmp_path):
+    """SetConf / Solve every step on the same solver objects (src/kernel/hydro.ipp:2351-2353):
+    one create, N solves"""
+    s, _ = systems.tlinear_system(16)
+    _, _, _, log = run(fake, tmp_path, s, tol=1e-6, maxiter=500, block=8, repeat=3)
+    assert sum(l.startswith("create") for l in log) == 1
+    assert sum(l.startswith("solve") for l in log) == 3
