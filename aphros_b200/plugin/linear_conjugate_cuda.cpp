@@ -18,6 +18,13 @@
 // solution back and requests the usual halo exchange of fc_sol
 // (src/linear/linear.ipp:116-118).  Unlike conjugate_cl it needs no shared-mesh
 // Comm, so it works under the native, local and cubismnc backends alike.
+//
+// Dimensions: the reference registers `conjugate` for every enabled
+// MeshCartesian<double,dim> (src/linear/linear.cpp:16-23).  The C ABI is a 3-D 7-point
+// solver; 1-D and 2-D meshes map onto it with ny and/or nz = 1, their rows
+// [c, x-, x+, (y-, y+,) const] widened to the 8-double format with zero coefficients in the
+// missing directions (a missing direction is neither periodic nor coupled).  4-D meshes are
+// not a 7-point problem and are not registered.
 #include <cstring>
 #include <iostream>
 #include <memory>
@@ -25,6 +32,7 @@
 #include <vector>
 
 #include "linear/linear.h"
+#include "util/macros.h"
 
 #include "aphcg.h"
 
@@ -40,12 +48,14 @@ class SolverCuda : public Solver<M> {
   using Expr = typename M::Expr;
   using MIdx = typename M::MIdx;
   enum class Method { conjugate, jacobi };
+  static constexpr int dim = int(M::dim);
 
   SolverCuda(const Conf& conf, Method method, bool maxnorm, int device, int ndevices,
              int slabs_per_device, unsigned flags, const M& m)
       : Base(conf), method_(method) {
-    static_assert(M::dim == 3, "conjugate_cuda: 3-D meshes only");
-    static_assert(sizeof(Expr) == 8 * sizeof(double), "row must be 8 doubles");
+    static_assert(dim >= 1 && dim <= 3, "conjugate_cuda: 1-D, 2-D and 3-D meshes");
+    static_assert(
+        sizeof(Expr) == (2 * dim + 2) * sizeof(double), "row must be 2*dim+2 doubles");
     if (m.IsLead()) {
       // one device object per rank, owned by the lead block
       // (cf. src/linear/conjugate_cl.ipp:29-35)
@@ -54,22 +64,22 @@ class SolverCuda : public Solver<M> {
       const auto& ms = m.GetShared();
       const MIdx size = ms.GetInBlockCells().GetSize();
       s.origin = ms.GetInBlockCells().GetBegin();
-      s.size = size;
+      for (int i = 0; i < dim; ++i) s.size[i] = size[i];
       aphcg_desc d;
       std::memset(&d, 0, sizeof(d));
-      d.nx = size[0];
-      d.ny = size[1];
-      d.nz = size[2];
+      d.nx = s.size[0];
+      d.ny = s.size[1];
+      d.nz = s.size[2];
       fassert(
           ms.GetGlobalSize() == size,
           "conjugate_cuda: one rank must own the whole domain (run aphros with "
           "px=py=pz=1 and set cuda_devices to use several GPUs from that rank)");
-      for (int i = 0; i < 3; ++i) d.periodic[i] = m.flags.is_periodic[i] ? 1 : 0;
+      for (int i = 0; i < dim; ++i) d.periodic[i] = m.flags.is_periodic[i] ? 1 : 0;
       d.cell_volume = m.GetCellSize().prod();
       d.rank = 0;
       d.nranks = 1;
       d.z0 = 0;
-      d.nz_local = size[2];
+      d.nz_local = s.size[2];
       d.flags = flags | (maxnorm ? APHCG_MAXNORM : 0);
       // the rank-wide index space is cut into `ndevices` z-slabs, one per GPU
       // device..device+ndevices-1, all driven from this (lead) block
@@ -81,7 +91,7 @@ class SolverCuda : public Solver<M> {
       for (int i = 0; i < ndevices; ++i)
         for (int k = 0; k < slabs_per_device; ++k) devices.push_back(device + i);
       Check(aphcg_group_create(&s.group, &d, devices.data(), (int32_t)devices.size()));
-      const uint64_t n = uint64_t(size[0]) * size[1] * size[2];
+      const uint64_t n = uint64_t(s.size[0]) * s.size[1] * s.size[2];
       Check(aphcg_host_alloc(reinterpret_cast<void**>(&s.rows), n * 8 * sizeof(double)));
       Check(aphcg_host_alloc(reinterpret_cast<void**>(&s.x), n * sizeof(double)));
       shared_ = &s;
@@ -113,7 +123,14 @@ class SolverCuda : public Solver<M> {
       // safe when blocks run concurrently under OpenMP, src/distr/distr.ipp:90-97)
       for (auto c : m.Cells()) {
         const size_t i = s.Index(m.GetIndexCells().GetMIdx(c));
-        std::memcpy(s.rows + 8 * i, &fc_system[c][0], 8 * sizeof(double));
+        if (dim == 3) {
+          std::memcpy(s.rows + 8 * i, &fc_system[c][0], 8 * sizeof(double));
+        } else {  // [c, x-, x+, (y-, y+,) const] -> [c, x-, x+, y-, y+, z-, z+, const]
+          const Expr& e = fc_system[c];
+          double* row = s.rows + 8 * i;
+          for (int k = 0; k < 7; ++k) row[k] = k < 2 * dim + 1 ? e[k] : 0.;
+          row[7] = e[2 * dim + 1];
+        }
         s.x[i] = fc_init ? (*fc_init)[c] : Scal(0);
       }
     }
@@ -168,11 +185,13 @@ class SolverCuda : public Solver<M> {
     double* rows = nullptr;  // pinned, rank-wide, [nz][ny][nx][8]
     double* x = nullptr;     // pinned, rank-wide, guess in / solution out
     MIdx origin;
-    MIdx size;
+    size_t size[3] = {1, 1, 1};  // rank-wide inner cells; 1 in the directions a mesh lacks
     Info info;
     size_t Index(MIdx w) const {
       const MIdx l = w - origin;
-      return (size_t(l[2]) * size[1] + l[1]) * size[0] + l[0];
+      size_t i = 0;
+      for (int d = dim - 1; d >= 0; --d) i = i * size[d] + size_t(l[d]);
+      return i;
     }
   };
   // CUDA / NCCL failures surface like any other aphros error
@@ -218,10 +237,11 @@ class ModuleLinearJacobiCuda : public ModuleLinear<M> {
   }
 };
 
-using M3 = MeshCartesian<double, 3>;
-bool kReg_conjugate_cuda[] = {
-    RegisterModule<ModuleLinearConjugateCuda<M3>>(),
-    RegisterModule<ModuleLinearJacobiCuda<M3>>(),
-};
+// one registration per enabled dimension, like src/linear/linear.cpp:16-23 (4-D excluded)
+#define X(dim)                                                               \
+  RegisterModule<ModuleLinearConjugateCuda<MeshCartesian<double, dim>>>(),   \
+      RegisterModule<ModuleLinearJacobiCuda<MeshCartesian<double, dim>>>(),
+bool kReg_conjugate_cuda[] = {MULTIDIMX1 MULTIDIMX2 MULTIDIMX3};
+#undef X
 
 } // namespace linear

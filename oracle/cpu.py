@@ -17,6 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcg_oracle.so")
 REF_DIR = os.path.join(_HERE, "_ref")
 REF_CG = os.path.join(REF_DIR, "ref_cg")
+REF_CG2 = REF_CG + "2"  # the same driver on MeshCartesian<double,2> (oracle/ref: make dim2)
 
 
 class _Desc(ctypes.Structure):
@@ -123,22 +124,29 @@ def have_reference():
     return os.path.exists(REF_CG)
 
 
+def have_reference_dim2():
+    return os.path.exists(REF_CG2)
+
+
 def solve_reference(system, x0=None, *, periodic=(True, True, True), tol=0.0, miniter=0,
                     maxiter=100, maxnorm=False, block=None, solver="conjugate",
-                    plugin=None, threads=1, repeat=1, extra="", env=None, workdir=None):
-    """Run the reference's own solver (oracle/_ref/ref_cg).
+                    plugin=None, threads=1, repeat=1, extra="", env=None, workdir=None, dim=3):
+    """Run the reference's own solver (oracle/_ref/ref_cg; dim=2: ref_cg2, a 2-D mesh,
+    system shape (1, ny, nx, 8) whose z coefficients are ignored).
 
     Returns (x, iter, residual, seconds).  Mesh extent is 1 (h = 1/max(n)).
     """
     system = np.ascontiguousarray(system, dtype=np.float64)
     nz, ny, nx = system.shape[:3]
+    if dim == 2 and nz != 1:
+        raise ValueError("a 2-D system has shape (1, ny, nx, 8)")
     b = block if block is not None else (nx, ny, nz)
     if isinstance(b, int):
         b = (b, b, b)
     with tempfile.TemporaryDirectory(dir=workdir) as tmp:
         fsys = os.path.join(tmp, "sys.f64")
         system.tofile(fsys)
-        cmd = [REF_CG, "--nx", str(nx), "--ny", str(ny), "--nz", str(nz),
+        cmd = [REF_CG2 if dim == 2 else REF_CG, "--nx", str(nx), "--ny", str(ny), "--nz", str(nz),
                "--bsx", str(b[0]), "--bsy", str(b[1]), "--bsz", str(b[2]),
                "--sys", fsys, "--out", os.path.join(tmp, "out"),
                "--tol", repr(float(tol)), "--maxiter", str(maxiter), "--miniter", str(miniter),

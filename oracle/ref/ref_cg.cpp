@@ -34,7 +34,13 @@
 #include "linear/linear.h"
 #include "util/distr.h"
 
-using M = MeshCartesian<double, 3>;
+// REFCG_DIM=2 (make dim2): the same driver on MeshCartesian<double,2>.  The file format stays
+// the 3-D one (nz = 1, rows of 8 doubles); the z coefficients of the file are ignored.
+#ifndef REFCG_DIM
+#define REFCG_DIM 3
+#endif
+constexpr int kDim = REFCG_DIM;
+using M = MeshCartesian<double, kDim>;
 using Scal = typename M::Scal;
 using MIdx = typename M::MIdx;
 using Expr = typename M::Expr;
@@ -94,7 +100,8 @@ void Run(M& m, Vars& var) {
   auto& t = *ctx;
   auto gidx = [&](IdxCell c) -> size_t {
     const MIdx w = m.GetIndexCells().GetMIdx(c);
-    return (size_t(w[2]) * g.ny + w[1]) * g.nx + w[0];
+    const size_t k = kDim > 2 ? size_t(w[kDim - 1]) : 0;
+    return (k * g.ny + w[1]) * g.nx + w[0];
   };
   if (sem("load")) {
     t.fc_system.Reinit(m, Expr(0));
@@ -102,9 +109,11 @@ void Run(M& m, Vars& var) {
     for (auto c : m.Cells()) {
       const size_t i = gidx(c);
       Expr e;
-      for (size_t k = 0; k < 8; ++k) {
+      // [c, x-, x+, y-, y+, (z-, z+,) const]
+      for (size_t k = 0; k < 2 * kDim + 1; ++k) {
         e[k] = g.sys[i * 8 + k];
       }
+      e[2 * kDim + 1] = g.sys[i * 8 + 7];
       t.fc_system[c] = e;
     }
     t.fc_sol.Reinit(m, 0);
@@ -198,7 +207,11 @@ int main(int argc, const char** argv) {
   const long bsx = atol(Arg(argc, argv, "--bsx", "16"));
   const long bsy = atol(Arg(argc, argv, "--bsy", Arg(argc, argv, "--bsx", "16")));
   const long bsz = atol(Arg(argc, argv, "--bsz", Arg(argc, argv, "--bsx", "16")));
-  if (g.nx % bsx || g.ny % bsy || g.nz % bsz) {
+  if (kDim == 2 && g.nz != 1) {
+    std::cerr << "ref_cg: the 2-D driver needs --nz 1" << std::endl;
+    return 2;
+  }
+  if (g.nx % bsx || g.ny % bsy || (kDim > 2 && g.nz % bsz)) {
     std::cerr << "ref_cg: mesh not divisible by block" << std::endl;
     return 2;
   }

@@ -131,3 +131,45 @@ def test_repeated_solves_reuse_the_device_object(fake, tmp_path):
     _, _, _, log = run(fake, tmp_path, s, tol=1e-6, maxiter=500, block=8, repeat=3)
     assert sum(l.startswith("create") for l in log) == 1
     assert sum(l.startswith("solve") for l in log) == 3
+
+
+PLUGIN2 = os.path.join(ROOT, "aphros_b200", "plugin", "libaphcg_aphros2.so")
+
+
+def system_2d(shape2, walls):
+    """a 2-D 5-point system in the 8-double row format: the generators' (1, ny, nx) system
+    with its z faces removed (their coefficients folded out of the diagonal)"""
+    ny, nx = shape2
+    if walls:
+        s, _ = systems.density_poisson_system(None, nspheres=3, seed=2, rho_in=0.2, shape=(1, ny, nx))
+    else:
+        s, _ = systems.tlinear_system(None, shape=(1, ny, nx))
+    s = s.copy()
+    s[..., 0] += s[..., 5] + s[..., 6]
+    s[..., 5:7] = 0.0
+    return s
+
+
+@pytest.mark.parametrize("walls", [False, True])
+def test_two_dimensional_mesh(fake, tmp_path, walls):
+    """MeshCartesian<double,2> (the reference registers `conjugate` for every enabled dimension,
+    src/linear/linear.cpp:16-23): 6-double rows widened to the 8-double format, nz = 1, the
+    missing direction neither periodic nor coupled; same answer as the reference's 2-D
+    `conjugate` over 4x4 blocks"""
+    from oracle import cpu
+    if not (cpu.have_reference_dim2() and os.path.exists(PLUGIN2)):
+        pytest.skip("2-D reference build (make -C oracle/ref dim2) not present")
+    s = system_2d((48, 64), walls)
+    per = (not walls, not walls, False)
+    kw = dict(periodic=per, tol=1e-9, maxiter=3000, block=(16, 12, 1), dim=2)
+    xr, itr, resr, _ = cpu.solve_reference(s, solver="conjugate", **kw)
+    log = str(tmp_path / "log2d.txt")
+    xg, itg, resg, _ = cpu.solve_reference(s, solver="conjugate_cuda", plugin=PLUGIN2,
+                                           env={"LD_PRELOAD": fake, "FAKE_APHCG_LOG": log}, **kw)
+    assert abs(itg - itr) <= 2 and resg < 1e-9
+    assert rel_max_abs(xg, xr) <= (1e-8 if walls else 1e-10)
+    create = [l for l in open(log).read().splitlines() if l.startswith("create")][0]
+    assert "nx=64 ny=48 nz=1 periodic=%d%d0" % (per[0], per[1]) in create
+    # cell "volume" of a 2-D mesh is the cell area (m.GetCellSize().prod(), mesh.h:171-173)
+    vol = float(re.search(r"volume=(\S+)", create).group(1))
+    assert abs(vol - (1.0 / 64) ** 2) < 1e-12
