@@ -29,7 +29,9 @@ MESH = "".join("set int %s %d\n" % kv for kv in [
 LINE = re.compile(r"linear\((\w+)\) '(\w+)': res=(\S+) iter=(\d+)")
 
 
-def run_app(tmp, solver, extra, steps):
+def run_app(tmp, solver, extra, steps, preload_first="", extra_env=None):
+    """preload_first / extra_env: used by tests/test_adapter_cpu.py to put a test double of the
+    C ABI in front of libaphcg.so"""
     d = os.path.join(tmp, solver)
     shutil.copytree(os.path.join(REF, "app202"), d)
     with open(os.path.join(d, "mesh.conf"), "w") as f:
@@ -42,7 +44,8 @@ def run_app(tmp, solver, extra, steps):
         f.write(extra)
     env = dict(os.environ, OMP_NUM_THREADS="8")
     if solver != "conjugate":
-        env["LD_PRELOAD"] = PLUGIN + ":" + env.get("LD_PRELOAD", "")
+        env["LD_PRELOAD"] = ":".join(x for x in (preload_first, PLUGIN, env.get("LD_PRELOAD", "")) if x)
+    env.update(extra_env or {})
     p = subprocess.run([os.path.join(REF, "ap.mfer"), "a.conf"], cwd=d, env=env,
                        capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
