@@ -203,3 +203,27 @@ def test_inapp_coalescence_over_the_test_double(fake, tmp_path):
     assert 101 in its and {26, 28} <= set(its)
     scale = np.abs(p_ref - p_ref.mean()).max()
     assert np.abs((p_dbl - p_dbl.mean()) - (p_ref - p_ref.mean())).max() <= 1e-3 * scale
+
+
+def test_inapp_taylor_couette_over_the_test_double(fake, tmp_path):
+    """examples/201_taylor_couette through ap.mfer with the adapter over the test double:
+    a 32x32x1 mesh (`dim 2`, periodic in z) with embedded boundaries -- identity rows for
+    excluded cells, a zero system for the third velocity component -- in 4 blocks of 16x16x1"""
+    import test_gpu_inapp as app
+    if not (os.path.exists(os.path.join(app.REF, "ap.mfer")) and os.path.isdir(os.path.join(app.REF, "app201"))):
+        pytest.skip("prebuilt ap.mfer / staged run directory not present")
+    log = str(tmp_path / "log_app201.txt")
+    extra = "set int hypre_symm_maxiter 1000\n"
+    kw = dict(app="app201", mesh=app.MESH_201)
+    s_ref, p_ref, _ = app.run_app(str(tmp_path), "conjugate", extra, 3, **kw)
+    s_dbl, p_dbl, _ = app.run_app(str(tmp_path), "conjugate_cuda", extra, 3, preload_first=fake,
+                                  extra_env={"FAKE_APHCG_LOG": log}, **kw)
+    lines = open(log).read().splitlines()
+    assert sum(l.startswith("create") for l in lines) == 1
+    assert "nx=32 ny=32 nz=1 periodic=001" in lines[0]
+    assert len(s_ref) == len(s_dbl) >= 12
+    for (_, sys_r, res_r, it_r), (name, sys_d, res_d, it_d) in zip(s_ref, s_dbl):
+        assert name == "conjugate_cuda" and sys_r == sys_d
+        assert abs(it_d - it_r) <= 2 and res_d < 1e-7, (sys_r, it_d, it_r, res_d)
+    scale = np.abs(p_ref - p_ref.mean()).max()
+    assert np.abs((p_dbl - p_dbl.mean()) - (p_ref - p_ref.mean())).max() <= 1e-6 * scale
