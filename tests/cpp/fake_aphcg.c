@@ -6,7 +6,10 @@
  * host logic -- the stage coroutine, block -> rank-wide gather/scatter, the geometry, flags,
  * Conf and device list it hands to the C ABI -- not any arithmetic.  The entry points the
  * adapter calls are answered by the CPU oracle (oracle/cg_oracle.c, test infrastructure) and
- * every call is logged to $FAKE_APHCG_LOG for the test to inspect.
+ * every call is logged to $FAKE_APHCG_LOG for the test to inspect.  With $FAKE_APHCG_TEE=<prefix>
+ * and $FAKE_APHCG_TEE_INDEX=<n> the n-th solve's inputs are also written to <prefix>.sys /
+ * <prefix>.x0 (raw float64): how a test captures a live system of the application (SURVEY.md 8d,
+ * input S1) to replay it through the real library.
  *
  * The real library has no CPU path: without a CUDA device aphcg_group_create fails.
  */
@@ -39,6 +42,10 @@ static void logf_(const char* fmt, ...) {
   fputc('\n', f);
   fclose(f);
 }
+
+static int g_solves = 0;
+
+static void tee(const aphcg_group_t* g, const double* system, const double* x0);
 
 static size_t ncell(const aphcg_group_t* g) {
   return (size_t)g->desc.nx * g->desc.ny * g->desc.nz;
@@ -98,6 +105,7 @@ int aphcg_group_solve(aphcg_group_t* g, const double* system, const aphcg_layout
                       const double* x0, const aphcg_layout* l0, double* x, const aphcg_layout* lx,
                       const aphcg_conf* conf, aphcg_info* info) {
   if (ls || l0 || lx) return APHCG_ERR_ARG; /* the adapter passes compact rank-wide arrays */
+  tee(g, system, x0);
   const cg_oracle_desc d = odesc(g, conf);
   /* x may alias x0 (linear.h:40): the oracle reads the guess before it writes x */
   double* guess = NULL;
@@ -159,4 +167,25 @@ int aphcg_group_download_solution(aphcg_group_t* g, double* x, const aphcg_layou
   memcpy(x, g->x, sizeof(double) * ncell(g));
   logf_("download_solution");
   return 0;
+}
+
+static void tee(const aphcg_group_t* g, const double* system, const double* x0) {
+  const char* prefix = getenv("FAKE_APHCG_TEE");
+  const char* index = getenv("FAKE_APHCG_TEE_INDEX");
+  const int n = g_solves++;
+  if (!prefix || !index || atoi(index) != n) return;
+  char path[1024];
+  snprintf(path, sizeof(path), "%s.sys", prefix);
+  FILE* f = fopen(path, "wb");
+  if (f) {
+    fwrite(system, sizeof(double), 8 * ncell(g), f);
+    fclose(f);
+  }
+  snprintf(path, sizeof(path), "%s.x0", prefix);
+  f = fopen(path, "wb");
+  if (f) {
+    if (x0) fwrite(x0, sizeof(double), ncell(g), f);
+    fclose(f);
+  }
+  logf_("tee solve %d -> %s.sys", n, prefix);
 }

@@ -132,3 +132,72 @@ def test_taylor_couette_embedded_boundaries(gpu, tmp_path):
         assert res_g < 1e-7
     scale = np.abs(p_ref - p_ref.mean()).max()
     assert np.abs((p_gpu - p_gpu.mean()) - (p_ref - p_ref.mean())).max() <= 1e-6 * scale
+
+
+def capture_pressure_system(tmp_path, index=6, steps=2):
+    """BASELINE config 1 / SURVEY.md 8d input S1: the pressure system of examples/202_coalescence
+    (64^3) as the application hands it to the solver, captured by running ap.mfer on the CPU with
+    the adapter over the tee-ing test double (tests/cpp/fake_aphcg.c).  index 6 = the first
+    pressure solve (after six zero-velocity solves of the start-up).  Returns
+    (system (64,64,64,8), x0 (64,64,64), cell_volume)."""
+    fake = str(tmp_path / "libfake_aphcg.so")
+    subprocess.run(["gcc", "-O2", "-fPIC", "-std=gnu99", "-ffp-contract=off", "-fno-fast-math", "-shared",
+                    "-o", fake, os.path.join(ROOT, "tests", "cpp", "fake_aphcg.c"),
+                    os.path.join(ROOT, "oracle", "cg_oracle.c"), "-lm"], check=True)
+    prefix = str(tmp_path / "tee")
+    log = str(tmp_path / "tee_log.txt")
+    run_app(str(tmp_path), "conjugate_cuda", "", steps, preload_first=fake,
+            extra_env={"FAKE_APHCG_LOG": log, "FAKE_APHCG_TEE": prefix,
+                       "FAKE_APHCG_TEE_INDEX": str(index)})
+    create = open(log).read().splitlines()[0]
+    vol = float(re.search(r"volume=(\S+)", create).group(1))
+    system = np.fromfile(prefix + ".sys", dtype=np.float64).reshape(64, 64, 64, 8)
+    x0 = np.fromfile(prefix + ".x0", dtype=np.float64).reshape(64, 64, 64)
+    return system, x0, vol
+
+
+def test_config1_captured_pressure_system(gpu, tmp_path):
+    """BASELINE config 1: "64^3 single-rank pressure Poisson (7-point, FP64, linsolver_symm =
+    conjugate) from one step of examples/202_coalescence".  The live system (two bubbles, density
+    ratio 100, walls) is captured from the application, then solved through the C ABI with the
+    example's own settings (tol 1e-2, miniter 10, maxiter 100 -> 101 iterations; the reference's
+    own log line for this run is `res=1.40709591e+00 iter=101`) and to convergence, against the
+    oracle."""
+    _need()
+    from aphros_b200 import Conf, Mesh, SolverConjugateCuda
+    from oracle import cpu
+    from cases import iterations_ok, rel_max_abs
+    system, x0, vol = capture_pressure_system(tmp_path)
+    per = (False, False, False)
+    m = Mesh(shape=(64, 64, 64), periodic=per, cell_volume=vol)
+
+    def oracle(tol, miniter, maxiter, block):
+        return cpu.solve(system, x0, periodic=per, cell_volume=vol, tol=tol, miniter=miniter,
+                         maxiter=maxiter, block=block)
+
+    # 1. the example's settings: runs into maxiter
+    conf = Conf(tol=1e-2, miniter=10, maxiter=100)
+    solver = SolverConjugateCuda(conf, {}, m)
+    x = x0.copy()
+    info = solver.Solve(system, x, x)
+    hist = solver.History(info.iter)
+    xo, it_o, res_o, hist_o = oracle(conf.tol, conf.miniter, conf.maxiter, 32)
+    assert info.iter == it_o == 101
+    assert abs(res_o - 1.40709591) < 1e-8            # the reference's log line, 9 digits
+    np.testing.assert_allclose(hist, hist_o, rtol=1e-6)
+    assert abs(info.residual - res_o) <= 1e-6 * res_o
+    assert rel_max_abs(x, xo) <= 1e-6
+    # 2. to 1e-7 of the initial residual: iteration count and solution against the oracle, within
+    #    the reference's own block-size spread (2926 / 2941 / 2930 iterations for 16^3 / 32^3 /
+    #    64^3 blocks, solutions 7e-8 apart: tests/cases.py explains the rule)
+    tol = 1e-7 * hist_o[0]
+    solver.SetConf(Conf(tol=tol, miniter=0, maxiter=20000))
+    x2 = x0.copy()
+    info2 = solver.Solve(system, x2, x2)
+    solver.close()
+    runs = [oracle(tol, 0, 20000, b) for b in (16, 32, 64)]
+    counts = [r[1] for r in runs]
+    assert max(counts) < 20000 and info2.residual < tol
+    assert iterations_ok(info2.iter, counts), (info2.iter, counts)
+    spread = max(rel_max_abs(r[0], runs[1][0]) for r in runs)
+    assert rel_max_abs(x2, runs[1][0]) <= max(1e-10, 4 * spread), (rel_max_abs(x2, runs[1][0]), spread)
