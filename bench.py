@@ -409,7 +409,6 @@ def main_ours(args):
         rows = capi.PinnedArray(mesh.local_shape + (8,))
         x0 = capi.PinnedArray(mesh.local_shape)
         xs = capi.PinnedArray(mesh.local_shape)
-        import ctypes
         capi.check(capi.lib().aphcg_download_system(solver._h, capi.ptr(rows.array), None))
         x0.array[...] = 0.0
         e2e_steps = max(1, min(args.steps, 3))

@@ -1,5 +1,5 @@
 """Per-iteration latency on small meshes for a few kernel configurations (GPU)."""
-import os, subprocess, sys, json
+import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CODE = r'''
 import sys, numpy as np
