@@ -120,19 +120,27 @@ class SolverCuda : public Solver<M> {
     if (sem("gather")) {
       auto& s = *shared_;
       // rows and guess of this block -> rank-wide pinned arrays (disjoint ranges,
-      // safe when blocks run concurrently under OpenMP, src/distr/distr.ipp:90-97)
-      for (auto c : m.Cells()) {
-        const size_t i = s.Index(m.GetIndexCells().GetMIdx(c));
+      // safe when blocks run concurrently under OpenMP, src/distr/distr.ipp:90-97).
+      // Cells of one x-row are contiguous both in the block's fields (x fastest,
+      // src/geom/block.h:149-158) and in the rank-wide arrays: whole rows are copied.
+      ForEachRow(m, [&](IdxCell c0, size_t i0, size_t n) {
+        const Expr* src = &fc_system[c0];
         if (dim == 3) {
-          std::memcpy(s.rows + 8 * i, &fc_system[c][0], 8 * sizeof(double));
+          std::memcpy(s.rows + 8 * i0, src, n * 8 * sizeof(double));
         } else {  // [c, x-, x+, (y-, y+,) const] -> [c, x-, x+, y-, y+, z-, z+, const]
-          const Expr& e = fc_system[c];
-          double* row = s.rows + 8 * i;
-          for (int k = 0; k < 7; ++k) row[k] = k < 2 * dim + 1 ? e[k] : 0.;
-          row[7] = e[2 * dim + 1];
+          for (size_t q = 0; q < n; ++q) {
+            const Expr& e = src[q];
+            double* row = s.rows + 8 * (i0 + q);
+            for (int k = 0; k < 7; ++k) row[k] = k < 2 * dim + 1 ? e[k] : 0.;
+            row[7] = e[2 * dim + 1];
+          }
         }
-        s.x[i] = fc_init ? (*fc_init)[c] : Scal(0);
-      }
+        if (fc_init) {
+          std::memcpy(s.x + i0, &(*fc_init)[c0], n * sizeof(double));
+        } else {
+          std::memset(s.x + i0, 0, n * sizeof(double));
+        }
+      });
     }
     if (sem("solve") && m.IsLead()) {
       auto& s = *shared_;
@@ -160,9 +168,9 @@ class SolverCuda : public Solver<M> {
       if (!fc_sol.size()) {
         fc_sol.Reinit(m);  // callers may pass an empty field (cf. opencl.h:36-40)
       }
-      for (auto c : m.Cells()) {
-        fc_sol[c] = s.x[s.Index(m.GetIndexCells().GetMIdx(c))];
-      }
+      ForEachRow(m, [&](IdxCell c0, size_t i0, size_t n) {
+        std::memcpy(&fc_sol[c0], s.x + i0, n * sizeof(double));
+      });
       t.info = s.info;
       m.Comm(&fc_sol, M::CommStencil::direct_one);
       if (m.flags.linreport && m.IsRoot()) {
@@ -194,6 +202,25 @@ class SolverCuda : public Solver<M> {
       return i;
     }
   };
+  // f(first cell of the row, its index in the rank-wide arrays, cells in the row) for every
+  // x-row of the block's inner cells
+  template <class F>
+  void ForEachRow(const M& m, F f) const {
+    const auto& bc = m.GetInBlockCells();
+    const MIdx b0 = bc.GetBegin(), bs = bc.GetSize();
+    const auto& ic = m.GetIndexCells();
+    size_t nrows = 1;
+    for (int d = 1; d < dim; ++d) nrows *= size_t(bs[d]);
+    for (size_t r = 0; r < nrows; ++r) {
+      MIdx w = b0;
+      size_t t = r;
+      for (int d = 1; d < dim; ++d) {
+        w[d] = b0[d] + int(t % size_t(bs[d]));
+        t /= size_t(bs[d]);
+      }
+      f(ic.GetIdx(w), shared_->Index(w), size_t(bs[0]));
+    }
+  }
   // CUDA / NCCL failures surface like any other aphros error
   // (fassert -> aphros_SetError + throw, src/util/logger.h:44-60)
   static void Check(int rc) {
