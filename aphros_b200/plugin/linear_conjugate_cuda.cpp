@@ -25,6 +25,7 @@
 // [c, x-, x+, (y-, y+,) const] widened to the 8-double format with zero coefficients in the
 // missing directions (a missing direction is neither periodic nor coupled).  4-D meshes are
 // not a 7-point problem and are not registered.
+#include <cstdio>
 #include <cstring>
 #include <iostream>
 #include <memory>
@@ -51,8 +52,9 @@ class SolverCuda : public Solver<M> {
   static constexpr int dim = int(M::dim);
 
   SolverCuda(const Conf& conf, Method method, bool maxnorm, int device, int ndevices,
-             int slabs_per_device, unsigned flags, const M& m)
-      : Base(conf), method_(method) {
+             int slabs_per_device, unsigned flags, const M& m, std::string dump = "",
+             int dump_index = 0)
+      : Base(conf), method_(method), dump_(dump), dump_index_(dump_index) {
     static_assert(dim >= 1 && dim <= 3, "conjugate_cuda: 1-D, 2-D and 3-D meshes");
     static_assert(
         sizeof(Expr) == (2 * dim + 2) * sizeof(double), "row must be 2*dim+2 doubles");
@@ -149,6 +151,10 @@ class SolverCuda : public Solver<M> {
       conf.miniter = this->conf.miniter;
       conf.maxiter = this->conf.maxiter;
       aphcg_info info;
+      if (!dump_.empty() && s.ncalls == dump_index_) {
+        DumpSystem(s, fc_system.GetName(), fc_init != nullptr, m);
+      }
+      ++s.ncalls;
       if (method_ == Method::conjugate) {
         // x doubles as guess and solution (fc_init may alias fc_sol, linear.h:40)
         Check(aphcg_group_solve(
@@ -195,6 +201,7 @@ class SolverCuda : public Solver<M> {
     MIdx origin;
     size_t size[3] = {1, 1, 1};  // rank-wide inner cells; 1 in the directions a mesh lacks
     Info info;
+    int ncalls = 0;  // Solve calls so far (selects the call to dump)
     size_t Index(MIdx w) const {
       const MIdx l = w - origin;
       size_t i = 0;
@@ -221,6 +228,33 @@ class SolverCuda : public Solver<M> {
       f(ic.GetIdx(w), shared_->Index(w), size_t(bs[0]));
     }
   }
+  // Capture of a live system for replay outside aphros (the reference's
+  // t.linear --system_out needs HDF5, src/test/linear/main.cpp:182-189): the rank-wide rows and
+  // guess exactly as they go to the C ABI, raw little-endian float64, plus a text header.
+  //   <prefix>.sys  nz*ny*nx*8   <prefix>.x0  nz*ny*nx (if a guess was given)   <prefix>.txt
+  // Replay: python -m aphros_b200.tlinear --replay <prefix> [--solver ...]
+  void DumpSystem(const Shared& s, const std::string& name, bool have_guess, const M& m) const {
+    const size_t n = s.size[0] * s.size[1] * s.size[2];
+    auto write = [&](const std::string& path, const double* p, size_t count) {
+      FILE* f = std::fopen(path.c_str(), "wb");
+      fassert(f, "conjugate_cuda: cannot write " + path);
+      const size_t put = std::fwrite(p, sizeof(double), count, f);
+      std::fclose(f);
+      fassert(put == count, "conjugate_cuda: short write to " + path);
+    };
+    write(dump_ + ".sys", s.rows, n * 8);
+    if (have_guess) write(dump_ + ".x0", s.x, n);
+    FILE* f = std::fopen((dump_ + ".txt").c_str(), "w");
+    fassert(f, "conjugate_cuda: cannot write " + dump_ + ".txt");
+    std::fprintf(f, "nx %zu\nny %zu\nnz %zu\n", s.size[0], s.size[1], s.size[2]);
+    std::fprintf(f, "periodic");
+    for (int i = 0; i < 3; ++i) std::fprintf(f, " %d", i < dim && m.flags.is_periodic[i] ? 1 : 0);
+    std::fprintf(f, "\ncell_volume %.17g\n", double(m.GetCellSize().prod()));
+    std::fprintf(f, "tol %.17g\nminiter %d\nmaxiter %d\n", double(this->conf.tol),
+                 this->conf.miniter, this->conf.maxiter);
+    std::fprintf(f, "guess %d\ncall %d\nname %s\n", have_guess ? 1 : 0, s.ncalls, name.c_str());
+    std::fclose(f);
+  }
   // CUDA / NCCL failures surface like any other aphros error
   // (fassert -> aphros_SetError + throw, src/util/logger.h:44-60)
   static void Check(int rc) {
@@ -228,6 +262,8 @@ class SolverCuda : public Solver<M> {
   }
 
   Method method_;
+  std::string dump_;  // linsolver_<prefix>_cuda_dump: file prefix, empty = off
+  int dump_index_ = 0;
   std::unique_ptr<Shared> shared_obj_;
   Shared* shared_ = nullptr;
 };
@@ -248,7 +284,8 @@ class ModuleLinearConjugateCuda : public ModuleLinear<M> {
     return std::make_unique<SolverCuda<M>>(
         this->GetConf(var, prefix), SolverCuda<M>::Method::conjugate, maxnorm,
         var.Int("cuda_device", 0), var.Int("cuda_devices", 1),
-        var.Int("cuda_slabs_per_device", 1), flags, m);
+        var.Int("cuda_slabs_per_device", 1), flags, m, var.String(key("cuda_dump"), ""),
+        var.Int(key("cuda_dump_index"), 0));
   }
 };
 

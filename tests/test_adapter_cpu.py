@@ -227,3 +227,24 @@ def test_inapp_taylor_couette_over_the_test_double(fake, tmp_path):
         assert abs(it_d - it_r) <= 2 and res_d < 1e-7, (sys_r, it_d, it_r, res_d)
     scale = np.abs(p_ref - p_ref.mean()).max()
     assert np.abs((p_dbl - p_dbl.mean()) - (p_ref - p_ref.mean())).max() <= 1e-6 * scale
+
+
+def test_capture_of_a_live_system(fake, tmp_path):
+    """`linsolver_symm_cuda_dump PREFIX` (+ `_cuda_dump_index N`): the adapter writes the
+    rank-wide rows and guess of the N-th Solve exactly as they go to the C ABI, with a text
+    header -- the raw stand-in for the reference's HDF5 `--system_out`"""
+    from aphros_b200 import tlinear
+    shape = (16, 24, 32)
+    s, _ = systems.density_poisson_system(None, nspheres=4, seed=3, rho_in=0.2, shape=shape)
+    x0 = np.random.default_rng(5).standard_normal(shape) * 1e-3
+    prefix = str(tmp_path / "cap")
+    extra = "set string linsolver_symm_cuda_dump %s\nset int linsolver_symm_cuda_dump_index 1" % prefix
+    run(fake, tmp_path, s, x0, periodic=(False, True, False), tol=1e-5, maxiter=77, miniter=3,
+        block=8, repeat=2, extra=extra)
+    meta, system, guess = tlinear.read_capture(prefix)
+    assert meta["shape"] == shape and meta["periodic"] == (False, True, False)
+    assert (meta["tol"], meta["miniter"], meta["maxiter"], meta["name"]) == (1e-5, 3, 77, "pressure")
+    assert np.array_equal(system, s) and np.array_equal(guess, x0)
+    from oracle import cpu
+    assert abs(meta["cell_volume"] - cpu.reference_cell_volume(shape, 8)) < 1e-20
+    assert "call 1" in open(prefix + ".txt").read()

@@ -153,3 +153,23 @@ def test_golden_vectors_on_gpu(gpu):
         # iteration more or less moves the solution by about tol x condition number;
         # the 1e-10 solution parity is asserted on converged solves in test_gpu_parity.py
         assert rel_max_abs(x, g["x"]) <= (1e-8 if fixed else 1e-5), (name, rel_max_abs(x, g["x"]))
+
+
+def test_capture_and_replay(gpu, tmp_path, capsys):
+    """a system captured from the reference driver by the adapter (`linsolver_symm_cuda_dump`)
+    replays through `python -m aphros_b200.tlinear --replay` to the same iteration count and
+    solution"""
+    cpu = _need()
+    from aphros_b200 import tlinear
+    s, _ = systems.tlinear_system(32)
+    prefix = str(tmp_path / "cap")
+    kw = dict(tol=1e-8, maxiter=2000, block=16)
+    xg, itg, resg, _ = cpu.solve_reference(
+        s, solver="conjugate_cuda", plugin=PLUGIN,
+        extra="set string linsolver_symm_cuda_dump %s" % prefix, **kw)
+    sol = str(tmp_path / "sol.raw")
+    assert tlinear.main(["--replay", prefix, "--solver", "conjugate_cuda", "--sol_out", sol]) == 0
+    out = capsys.readouterr().out
+    assert "iter=%d" % itg in out
+    x = np.fromfile(sol, dtype=np.float64).reshape(32, 32, 32)
+    assert rel_max_abs(x, xg) <= 1e-12   # same library, same inputs
