@@ -175,8 +175,8 @@ int aphcg_download_system(aphcg_t* h, double* system, const aphcg_layout* layout
  * Residual halo planes are written straight into the neighbour's ghost planes
  * over NVLink, and the two scalars per iteration are all-reduced through small
  * "mailboxes" in every rank's memory, written by the kernel that finishes the
- * local reduction (peer memory again; NCCL is used once per solve, for the
- * initial residual and as a barrier).  Wiring, once after create:
+ * local reduction (peer memory again; NCCL is used only at the start of a
+ * solve, outside the loop: for the initial residual and as a barrier).  Wiring, once after create:
  *   1. rank 0: aphcg_comm_unique_id(id); broadcast id to all ranks (the host
  *      harness does this with torch.distributed / MPI / a file);
  *   2. every rank: aphcg_comm_init(h, id)              (collective)
