@@ -94,7 +94,14 @@ __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-template <int TXT, bool kSingle, bool kSym>
+// kDefer (symmetric storage only; OPT-IN via APHCG_DEFER=1, prepared at the end of round 1
+// without GPU access and therefore not the default): everything that merely CONSUMES a freshly
+// loaded coefficient -- the lane shuffle for x+, the y-/z- register aliases -- is moved from the
+// load section to just in front of the stencil, behind the plane barrier, so that a warp issues
+// all loads of a step back to back and their latency overlaps the p_new phase
+// (profiles/r01d_dir_spmv_stalls_by_line.md: 22 % of the stall samples sit on those consumers).
+// Same values into the same FMAs.
+template <int TXT, bool kSingle, bool kSym, bool kDefer = false>
 __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
     k_dir_spmv_tma(const Geom g, const DevPtrs d, const int zc, const int pd, const int opts,
                    const __grid_constant__ CUtensorMap map_r,
@@ -231,18 +238,31 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
             const int64_t idc = ci + cj[h] * g.cy + (int64_t)m * g.cz;
             a[h][0] = ldv_stream<2>(d.a[0] + idc);
             a[h][1] = ldv_stream<2>(d.a[1] + idc);
-            a[h][3] = (h == 1) ? a[0][4] : ldv_stream<2>(d.a[3] + idc);
+            if constexpr (!kDefer) {
+              a[h][3] = (h == 1) ? a[0][4] : ldv_stream<2>(d.a[3] + idc);
+            } else {
+              if (h == 0) a[0][3] = ldv_stream<2>(d.a[3] + idc);  // a[1][3] = a[0][4]: later
+            }
             // y+: next row's y-, or this row's own y+ on the last row of the domain
             a[h][4] = (cj[h] + 1 < g.ny) ? ldv<2>(d.a[3] + idc + g.cy) : ldv_stream<2>(d.a[4] + idc);
             // z-: carried from the previous plane (its z+), except on the first plane
             a[h][5] = (n == 2) ? ldv_stream<2>(d.a[5] + idc) : zcarry[h];
             a[h][6] = (m + 1 < g.nzl) ? ldv_stream<2>(d.a[5] + idc + g.cz) : ldv_stream<2>(d.a[6] + idc);
-            zcarry[h] = a[h][6];
+            if constexpr (!kDefer) {
+              zcarry[h] = a[h][6];
+            } else {
+              // the two x+ values that do not come from the next lane are loads: issue them now
+              if (ci + 2 >= g.nx) {
+                a[h][2].v[1] = d.a[2][idc + 1];  // last cell of the row: its own x+
+              } else if (lane == 31) {
+                a[h][2].v[1] = d.a[1][idc + 2];  // next lane lives in another warp / CTA
+              }
+            }
           }
         }
         // x+ of the second cell of the pair = x- of the next lane's first cell
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2 && !kDefer; ++h) {
           const double from_next = __shfl_down_sync(0xffffffffu, a[h][1].v[0], 1);
           if (act[h]) {
             const int64_t idc = ci + cj[h] * g.cy + (int64_t)m * g.cz;
@@ -336,6 +356,18 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
       const double* rc = smd + (2 * S + (n + RING - 1) % RING) * BOXD;  // plane m
       const double* rm = smd + (2 * S + (n + RING - 2) % RING) * BOXD;  // plane m-1
       const double* rp = rg;                                            // plane m+1
+      if constexpr (kSym && kDefer) {
+        // the consumers of this step's coefficient loads, deferred to here (see kDefer)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double from_next = __shfl_down_sync(0xffffffffu, a[h][1].v[0], 1);
+          if (act[h]) {
+            if (h == 1) a[1][3] = a[0][4];
+            a[h][2].v[0] = a[h][1].v[1];
+            if (ci + 2 < g.nx && lane != 31) a[h][2].v[1] = from_next;
+          }
+        }
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (act[h]) {
@@ -367,6 +399,7 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
           ap.v[1] = t;
           acc = fma(pc.y, t, acc);
           stv_stream<2>(d.ap + ci + cj[h] * g.cy + (int64_t)m * g.cz, ap);
+          if constexpr (kSym && kDefer) zcarry[h] = a[h][6];  // z+ becomes z- of the next plane
         }
       }
     }
@@ -398,7 +431,7 @@ struct TmaPlan {
   dim3 grid;
   int zc;
   int pd;  // L2 prefetch distance in planes (0 = off)
-  int opts;  // bit 0: streaming stores of p_new
+  int opts;  // bit 0: streaming stores of p_new; bit 1: kDefer variant of the symmetric kernel
   int tx;  // tile width in use (64 or 128)
 };
 
@@ -412,6 +445,10 @@ static bool set_smem_limit() {
          cudaFuncSetAttribute(k_dir_spmv_tma<TXT, true, true>,
                               cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess &&
          cudaFuncSetAttribute(k_dir_spmv_tma<TXT, false, true>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess &&
+         cudaFuncSetAttribute(k_dir_spmv_tma<TXT, true, true, true>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess &&
+         cudaFuncSetAttribute(k_dir_spmv_tma<TXT, false, true, true>,
                               cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess;
 }
 
@@ -480,6 +517,7 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
   if (const char* ep = getenv("APHCG_PREFETCH")) p->pd = atoi(ep);
   p->opts = 1;  // streaming p_new stores: 1.87 vs 1.90 ms at 512^3
   if (const char* eo = getenv("APHCG_PSTREAM")) p->opts = atoi(eo) ? 1 : 0;
+  if (const char* ed = getenv("APHCG_DEFER")) p->opts |= atoi(ed) ? 2 : 0;
   p->grid = dim3((g.nx + TX - 1) / TX, (g.ny + TY - 1) / TY, (g.nzl + zc - 1) / zc);
   if (!(TX == 64 ? set_smem_limit<64>() : set_smem_limit<128>())) {
     cudaGetLastError();
@@ -492,21 +530,27 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
 void tma_plan_destroy(TmaPlan* p) { delete p; }
 unsigned tma_plan_blocks(const TmaPlan* p) { return p->grid.x * p->grid.y * p->grid.z; }
 void tma_plan_describe(const TmaPlan* p, char* buf, int buflen) {
-  snprintf(buf, buflen, "tile=%dx%d planes_per_cta=%d stages=%d l2_prefetch=%d pstream=%d ctas=%u",
-           p->tx, TY, p->zc, S, p->pd, p->opts & 1, tma_plan_blocks(p));
+  snprintf(buf, buflen, "tile=%dx%d planes_per_cta=%d stages=%d l2_prefetch=%d pstream=%d%s ctas=%u",
+           p->tx, TY, p->zc, S, p->pd, p->opts & 1, (p->opts & 2) ? " defer=1" : "",
+           tma_plan_blocks(p));
 }
 
 template <int TXT>
 static void launch_cfg(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool single, bool sym,
                        cudaStream_t s) {
   using C = Cfg<TXT>;
-#define APHCG_LAUNCH_TMA(SINGLE, SYM)                                                    \
-  k_dir_spmv_tma<TXT, SINGLE, SYM><<<p->grid, C::NT, C::kSmemBytes, s>>>(g, d, p->zc, p->pd, p->opts, \
-                                                                         p->map_r, p->map_p0, p->map_p1)
+#define APHCG_LAUNCH_TMA(SINGLE, SYM, DEFER)                                                    \
+  k_dir_spmv_tma<TXT, SINGLE, SYM, DEFER><<<p->grid, C::NT, C::kSmemBytes, s>>>(                  \
+      g, d, p->zc, p->pd, p->opts, p->map_r, p->map_p0, p->map_p1)
+  const bool defer = sym && (p->opts & 2) != 0;
   if (single) {
-    if (sym) APHCG_LAUNCH_TMA(true, true); else APHCG_LAUNCH_TMA(true, false);
+    if (defer) APHCG_LAUNCH_TMA(true, true, true);
+    else if (sym) APHCG_LAUNCH_TMA(true, true, false);
+    else APHCG_LAUNCH_TMA(true, false, false);
   } else {
-    if (sym) APHCG_LAUNCH_TMA(false, true); else APHCG_LAUNCH_TMA(false, false);
+    if (defer) APHCG_LAUNCH_TMA(false, true, true);
+    else if (sym) APHCG_LAUNCH_TMA(false, true, false);
+    else APHCG_LAUNCH_TMA(false, false, false);
   }
 #undef APHCG_LAUNCH_TMA
 }
