@@ -491,8 +491,10 @@ def test_wide_meshes_with_walls(gpu, shape):
     assert rel_max_abs(x, xo) <= X_TOL
 
 
-@pytest.mark.xfail(strict=False, reason="opt-in kernel variant written after the round's GPU budget "
-                   "ended; never run on a GPU yet (the default kernels' SASS is unchanged by it)")
+@pytest.mark.skipif(__import__("os").environ.get("APHCG_TEST_DEFER") != "1",
+                    reason="opt-in kernel variant written after the round's GPU budget ended and "
+                           "never run on a GPU yet: run with APHCG_TEST_DEFER=1 (the default "
+                           "kernels' SASS is unchanged by it)")
 def test_deferred_consumption_variant_is_bitwise_identical(gpu, monkeypatch):
     """APHCG_DEFER=1: the symmetric-storage direction kernel with the consumers of the
     coefficient loads (lane shuffle for x+, y-/z- aliases) moved behind the plane barrier
