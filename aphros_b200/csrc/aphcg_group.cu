@@ -11,6 +11,7 @@
 // collective steps of a solve use a thread barrier (cg_group.h) instead of NCCL.
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <functional>
 #include <string>
 #include <thread>
@@ -55,7 +56,16 @@ int RunAll(aphcg_group* g, const std::function<int(int)>& fn) {
   };
   std::vector<std::thread> th;
   th.reserve(g->n - 1);
-  for (int q = 1; q < g->n; ++q) th.emplace_back(body, q);
+  try {
+    for (int q = 1; q < g->n; ++q) th.emplace_back(body, q);
+  } catch (const std::exception& e) {
+    // a slab thread could not be started: release the ones that run (they would wait for it
+    // at the first barrier) and give up
+    g->gs->Abort();
+    for (auto& t : th) t.join();
+    g->broken = true;
+    return GroupFail(APHCG_ERR_STATE, std::string("cannot start a slab thread: ") + e.what());
+  }
   body(0);
   for (auto& t : th) t.join();
   // report the slab that failed on its own, not a peer that only saw the abort
