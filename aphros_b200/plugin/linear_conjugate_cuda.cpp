@@ -17,7 +17,9 @@
 // talks to the GPU, inside ONE stage; every block then copies its part of the
 // solution back and requests the usual halo exchange of fc_sol
 // (src/linear/linear.ipp:116-118).  Unlike conjugate_cl it needs no shared-mesh
-// Comm, so it works under the native, local and cubismnc backends alike.
+// Comm, so it does not depend on the backend: tested under native and local; cubismnc
+// (not buildable here) provides the same base-class services it uses
+// (BcastFromLead, block-level Comm; src/distr/distr.ipp:171-282).
 //
 // Dimensions: the reference registers `conjugate` for every enabled
 // MeshCartesian<double,dim> (src/linear/linear.cpp:16-23).  The C ABI is a 3-D 7-point
