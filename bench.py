@@ -398,6 +398,12 @@ def main_ours(args):
             "ms_per_launch": ms_dir, "peak_source": peak_src,
             "update_kernel": {"ms_per_launch": ms_upd,
                               "achieved": B_ALG_UPDATE * cells_local / (ms_upd * 1e-3) / 1e9},
+            # what the HBM actually moved (ncu DRAM bytes of the committed capture / live time):
+            # below the algorithmic figure because symmetric storage reads 4 of the 7 coefficients
+            "dram": (None if not measured_traffic(cells_local, solver.Describe().split(" ")[0]) else {
+                "bytes_per_launch": measured_traffic(cells_local, solver.Describe().split(" ")[0]),
+                "achieved": measured_traffic(cells_local, solver.Describe().split(" ")[0]) / (ms_dir * 1e-3) / 1e9,
+                "frac": measured_traffic(cells_local, solver.Describe().split(" ")[0]) / (ms_dir * 1e-3) / 1e9 / peak}),
             "iteration": {"algorithmic_bytes_per_cell": B_ALG,
                           "achieved": B_ALG * cells * iters / (loop_ms * 1e-3) / 1e9,
                           "frac": B_ALG * cells * iters / (loop_ms * 1e-3) / 1e9 / peak},
