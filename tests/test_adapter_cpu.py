@@ -248,3 +248,23 @@ def test_capture_of_a_live_system(fake, tmp_path):
     from oracle import cpu
     assert abs(meta["cell_volume"] - cpu.reference_cell_volume(shape, 8)) < 1e-20
     assert "call 1" in open(prefix + ".txt").read()
+
+
+def test_captured_config1_system_reproduces_the_reference_log(fake, tmp_path):
+    """BASELINE config 1 on the CPU side: the 64^3 pressure system of example 202 captured from
+    the application (tee of the test double), solved by the oracle with the example's settings,
+    gives the reference's own log line `res=1.40709591e+00 iter=101` (8 blocks of 32^3); the
+    system is bitwise symmetric with zero wall coefficients, i.e. 4-stream storage applies"""
+    import test_gpu_inapp as app
+    from oracle import cpu
+    if not (os.path.exists(os.path.join(app.REF, "ap.mfer")) and os.path.isdir(os.path.join(app.REF, "app202"))):
+        pytest.skip("prebuilt ap.mfer / staged run directory not present")
+    s, x0, vol = app.capture_pressure_system(tmp_path)
+    assert vol == 0.001953125 and not x0.any()
+    _, it, res, _ = cpu.solve(s, x0, periodic=(False, False, False), cell_volume=vol, tol=1e-2,
+                              miniter=10, maxiter=100, block=32)
+    assert it == 101 and abs(res - 1.40709591) < 5e-9
+    assert np.array_equal(s[:, :, :-1, 2], s[:, :, 1:, 1])
+    assert np.array_equal(s[:, :-1, :, 4], s[:, 1:, :, 3])
+    assert np.array_equal(s[:-1, :, :, 6], s[1:, :, :, 5])
+    assert not s[:, :, 0, 1].any() and not s[:, :, -1, 2].any() and not s[0, :, :, 5].any()
