@@ -519,3 +519,54 @@ def test_deferred_consumption_variant_is_bitwise_identical(gpu, monkeypatch):
             assert ("defer=1" in desc) == (flag == "1" and "sym4" in desc), desc
             out.append((x, hist))
         assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), shape
+
+
+def test_device_resident_inputs_and_outputs(gpu):
+    """aphcg_set_system_device / aphcg_set_guess_device / aphcg_get_solution_device: rows, guess
+    and solution as DEVICE pointers (what a caller that assembles on the GPU would pass), compact
+    and laid out like a reference field with halos; same bits as the host-buffer path"""
+    import ctypes
+    import torch
+    case = case_density(24, rho_in=0.1)
+    shape = case["system"].shape[:3]
+    n, hl = 24, 2
+    x0 = random_guess(shape)
+    conf = Conf(tol=0.0, miniter=0, maxiter=30)
+    m = Mesh(shape=shape, periodic=case["periodic"])
+    x_host, info_host, _ = gpu_solve(case, conf, x0=x0)
+    L = capi.lib()
+    dev = torch.device("cuda", 0)
+    for padded in (False, True):
+        solver = SolverConjugateCuda(conf, {}, m)
+        if padded:
+            full = n + 2 * hl + 1
+            sys_full = np.full((full, full, full, 8), np.nan)
+            sys_full[hl:hl + n, hl:hl + n, hl:hl + n] = case["system"]
+            g_full = np.full((full, full, full), np.nan)
+            g_full[hl:hl + n, hl:hl + n, hl:hl + n] = x0
+            off = hl * (1 + full + full * full)
+            lay = capi.Layout(off, full, full * full)
+            d_sys, d_x0 = torch.from_numpy(sys_full).to(dev), torch.from_numpy(g_full).to(dev)
+            d_x = torch.full((full, full, full), 777.0, dtype=torch.float64, device=dev)
+            pl = ctypes.byref(lay)
+        else:
+            d_sys = torch.from_numpy(np.ascontiguousarray(case["system"])).to(dev)
+            d_x0 = torch.from_numpy(x0).to(dev)
+            d_x = torch.zeros(shape, dtype=torch.float64, device=dev)
+            pl = None
+        torch.cuda.synchronize()   # the library works on its own stream
+        capi.check(L.aphcg_set_system_device(solver._h, ctypes.c_void_p(d_sys.data_ptr()), pl))
+        capi.check(L.aphcg_set_guess_device(solver._h, ctypes.c_void_p(d_x0.data_ptr()), pl))
+        info = solver.Run()
+        capi.check(L.aphcg_get_solution_device(solver._h, ctypes.c_void_p(d_x.data_ptr()), pl))
+        solver.close()
+        out = d_x.cpu().numpy()
+        if padded:
+            inner = out[hl:hl + n, hl:hl + n, hl:hl + n]
+            mask = np.ones_like(out, dtype=bool)
+            mask[hl:hl + n, hl:hl + n, hl:hl + n] = False
+            assert (out[mask] == 777.0).all(), "cells outside the inner block were touched"
+        else:
+            inner = out
+        assert info.iter == info_host.iter and info.residual == info_host.residual
+        assert np.array_equal(inner, x_host)
