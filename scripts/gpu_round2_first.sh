@@ -7,7 +7,7 @@
 #      at 512^3 and the small-mesh latencies.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -rf \
-  -k "two_dimensional or taylor_couette or config1 or capture_and_replay or wide_meshes" \
+  -k "two_dimensional or taylor_couette or config1 or capture_and_replay or wide_meshes or device_resident" \
   > gpurun_out/r2_new_tests.log 2>&1
 tail -15 gpurun_out/r2_new_tests.log
 APHCG_TEST_DEFER=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -rf -k deferred_consumption \
