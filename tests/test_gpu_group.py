@@ -50,6 +50,7 @@ def test_group_matches_oracle_tlinear(gpu, devices):
     solver = SolverConjugateCudaGroup(conf, {}, Mesh(shape=shape, periodic=case["periodic"]),
                                       devices)
     assert sum(n for _, n in solver.Slabs()) == shape[0]
+    assert capi.lib().aphcg_group_size(solver._g) == len(devices)
     x = x0.copy()
     info = solver.Solve(case["system"], x, x)  # fc_init == &fc_sol (linear.h:40)
     xo, it_o, res_o, hist_o = oracle_solve(case, x0, tol=tol, miniter=0, maxiter=3000)

@@ -555,6 +555,7 @@ def test_device_resident_inputs_and_outputs(gpu):
             d_x = torch.zeros(shape, dtype=torch.float64, device=dev)
             pl = None
         torch.cuda.synchronize()   # the library works on its own stream
+        assert L.aphcg_stream(solver._h), "the handle's cudaStream_t, for callers timing with events"
         capi.check(L.aphcg_set_system_device(solver._h, ctypes.c_void_p(d_sys.data_ptr()), pl))
         capi.check(L.aphcg_set_guess_device(solver._h, ctypes.c_void_p(d_x0.data_ptr()), pl))
         info = solver.Run()

@@ -80,6 +80,8 @@ def test_group_sync_barrier(tmp_path):
 
 def test_argument_checks(built):
     L = capi.lib()
+    assert L.aphcg_group_size(None) == 0 and L.aphcg_stream(None) is None
+    assert L.aphcg_group_member(None, 0) is None and L.aphcg_launch_count(None) == 0
     h = ctypes.c_void_p()
     d = capi.Desc()
     d.nx, d.ny, d.nz = 0, 4, 4
