@@ -28,6 +28,7 @@
 // missing directions (a missing direction is neither periodic nor coupled).  4-D meshes are
 // not a 7-point problem and are not registered.
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <iostream>
 #include <memory>
@@ -39,7 +40,26 @@
 
 #include "aphcg.h"
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 namespace linear {
+
+// Copy into the rank-wide staging arrays with non-temporal stores: the destination is written
+// once and next read by the GPU's copy engine, so it should not displace the block's working
+// set from the caches (nor be read for ownership first).  dst must be 16-byte aligned.
+inline void StreamCopy(double* dst, const double* src, size_t n) {
+#if defined(__SSE2__)
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    size_t i = 0;
+    for (; i + 2 <= n; i += 2) _mm_stream_pd(dst + i, _mm_loadu_pd(src + i));
+    for (; i < n; ++i) dst[i] = src[i];
+    return;
+  }
+#endif
+  std::memcpy(dst, src, n * sizeof(double));
+}
 
 template <class M>
 class SolverCuda : public Solver<M> {
@@ -130,7 +150,7 @@ class SolverCuda : public Solver<M> {
       ForEachRow(m, [&](IdxCell c0, size_t i0, size_t n) {
         const Expr* src = &fc_system[c0];
         if (dim == 3) {
-          std::memcpy(s.rows + 8 * i0, src, n * 8 * sizeof(double));
+          StreamCopy(s.rows + 8 * i0, &(*src)[0], n * 8);
         } else {  // [c, x-, x+, (y-, y+,) const] -> [c, x-, x+, y-, y+, z-, z+, const]
           for (size_t q = 0; q < n; ++q) {
             const Expr& e = src[q];
@@ -145,6 +165,9 @@ class SolverCuda : public Solver<M> {
           std::memset(s.x + i0, 0, n * sizeof(double));
         }
       });
+#if defined(__SSE2__)
+      _mm_sfence();  // the streamed rows are globally visible before the next stage reads them
+#endif
     }
     if (sem("solve") && m.IsLead()) {
       auto& s = *shared_;
