@@ -109,7 +109,7 @@ int aphcg_group_solve(aphcg_group_t* g, const double* system, const aphcg_layout
   const cg_oracle_desc d = odesc(g, conf);
   /* x may alias x0 (linear.h:40): the oracle reads the guess before it writes x */
   double* guess = NULL;
-  if (x0) {
+  if (x0 && !getenv("FAKE_APHCG_NOSOLVE")) {
     guess = (double*)malloc(sizeof(double) * ncell(g));
     memcpy(guess, x0, sizeof(double) * ncell(g));
   }
