@@ -487,10 +487,11 @@ class ModuleLinearConjugateCuda(ModuleLinear):
         if int(var.get("linsolver_" + prefix + "_cuda_tma", 1)) == 0:
             flags |= capi.APHCG_NO_TMA
         ndev = int(var.get("cuda_devices", 1))
-        if ndev > 1:  # one process, several GPUs: z-slabs on devices cuda_device..+ndev-1
+        per_dev = int(var.get("cuda_slabs_per_device", 1))
+        if ndev * per_dev > 1:  # one process, several z-slabs: devices cuda_device..+ndev-1
             first = int(var.get("cuda_device", 0))
-            return SolverConjugateCudaGroup(self.GetConf(var, prefix), extra, m,
-                                            range(first, first + ndev), flags)
+            devices = [first + i for i in range(ndev) for _ in range(per_dev)]
+            return SolverConjugateCudaGroup(self.GetConf(var, prefix), extra, m, devices, flags)
         return SolverConjugateCuda(self.GetConf(var, prefix), extra, m, flags)
 
 

@@ -170,10 +170,11 @@ def test_group_jacobi(gpu, devices):
 def test_group_through_the_factory(gpu):
     """`cuda_devices` on the reference's factory path (ModuleLinear::Make)"""
     case = case_tlinear(16)
-    var = {"hypre_symm_tol": 1e-6, "hypre_symm_maxiter": 500, "cuda_devices": 2,
-           "cuda_device": 0}
-    if capi.device_count() < 2:
-        pytest.skip("the factory maps slabs to consecutive devices: needs 2 GPUs")
+    var = {"hypre_symm_tol": 1e-6, "hypre_symm_maxiter": 500, "cuda_device": 0}
+    if capi.device_count() >= 2:
+        var["cuda_devices"] = 2          # slabs on consecutive devices
+    else:
+        var["cuda_slabs_per_device"] = 2  # two slabs on the one GPU
     s = ModuleLinear.GetInstance("conjugate_cuda").Make(var, "symm", Mesh(shape=(16, 16, 16)))
     assert isinstance(s, SolverConjugateCudaGroup)
     x = np.zeros((16, 16, 16))

@@ -67,6 +67,10 @@ def test_group_argument_checks_and_partition(built):
     var = {"hypre_symm_tol": 1e-3, "hypre_symm_maxiter": 10, "cuda_devices": 20}
     with pytest.raises(capi.AphcgError, match="1..16 slabs"):
         mod.Make(var, "symm", Mesh(shape=(64, 8, 8)))
+    var = {"hypre_symm_tol": 1e-3, "hypre_symm_maxiter": 10, "cuda_devices": 3,
+           "cuda_slabs_per_device": 6}
+    with pytest.raises(capi.AphcgError, match="1..16 slabs"):
+        mod.Make(var, "symm", Mesh(shape=(64, 8, 8)))
 
 
 def test_group_sync_barrier(tmp_path):
