@@ -10,7 +10,7 @@ timeout 900 python -m pytest tests -m gpu -q -rf \
   -k "two_dimensional or taylor_couette or config1 or capture_and_replay or wide_meshes or device_resident" \
   > gpurun_out/r2_new_tests.log 2>&1
 tail -15 gpurun_out/r2_new_tests.log
-APHCG_TEST_DEFER=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -rf -k deferred_consumption \
+APHCG_TEST_DEFER=1 timeout 300 python -m pytest tests/test_gpu_z_late.py -q -rf -k deferred_consumption \
   > gpurun_out/r2_defer_test.log 2>&1
 tail -5 gpurun_out/r2_defer_test.log
 scripts/gpu_sweep_env.sh APHCG_DEFER=0 APHCG_DEFER=1 APHCG_DEFER=1,APHCG_PREFETCH=1 APHCG_DEFER=1,APHCG_PREFETCH=3

@@ -62,30 +62,6 @@ def test_module_over_several_slabs(gpu, solver):
         assert rel_max_abs(xg, xr) <= (1e-10 if solver == "conjugate" else 1e-9), extra
 
 
-@pytest.mark.parametrize("walls", [False, True])
-def test_two_dimensional_mesh(gpu, walls):
-    """MeshCartesian<double,2>: the adapter widens the 6-double rows to the C ABI's 8-double
-    format (nz = 1, no coupling and no periodicity in the missing direction); the reference's
-    own 2-D `conjugate` over 4x4 blocks is the checker (oracle/_ref/ref_cg2)"""
-    cpu = _need()
-    plugin2 = PLUGIN[:-3] + "2.so"
-    if not (cpu.have_reference_dim2() and os.path.exists(plugin2)):
-        pytest.skip("2-D reference build (make -C oracle/ref dim2) not present")
-    ny, nx = 48, 64
-    if walls:
-        s, _ = systems.density_poisson_system(None, nspheres=3, seed=2, rho_in=0.2, shape=(1, ny, nx))
-    else:
-        s, _ = systems.tlinear_system(None, shape=(1, ny, nx))
-    s = s.copy()
-    s[..., 0] += s[..., 5] + s[..., 6]   # fold the z faces out: a 5-point system
-    s[..., 5:7] = 0.0
-    per = (not walls, not walls, False)
-    kw = dict(periodic=per, tol=1e-9, maxiter=3000, block=(16, 12, 1), dim=2)
-    xr, itr, resr, _ = cpu.solve_reference(s, solver="conjugate", **kw)
-    xg, itg, resg, _ = cpu.solve_reference(s, solver="conjugate_cuda", plugin=plugin2, **kw)
-    assert abs(itg - itr) <= 2 and resg < 1e-9
-    assert rel_max_abs(xg, xr) <= (1e-8 if walls else 1e-10)
-
 
 def test_guess_nonperiodic_and_maxnorm(gpu):
     cpu = _need()
@@ -153,23 +129,3 @@ def test_golden_vectors_on_gpu(gpu):
         # iteration more or less moves the solution by about tol x condition number;
         # the 1e-10 solution parity is asserted on converged solves in test_gpu_parity.py
         assert rel_max_abs(x, g["x"]) <= (1e-8 if fixed else 1e-5), (name, rel_max_abs(x, g["x"]))
-
-
-def test_capture_and_replay(gpu, tmp_path, capsys):
-    """a system captured from the reference driver by the adapter (`linsolver_symm_cuda_dump`)
-    replays through `python -m aphros_b200.tlinear --replay` to the same iteration count and
-    solution"""
-    cpu = _need()
-    from aphros_b200 import tlinear
-    s, _ = systems.tlinear_system(32)
-    prefix = str(tmp_path / "cap")
-    kw = dict(tol=1e-8, maxiter=2000, block=16)
-    xg, itg, resg, _ = cpu.solve_reference(
-        s, solver="conjugate_cuda", plugin=PLUGIN,
-        extra="set string linsolver_symm_cuda_dump %s" % prefix, **kw)
-    sol = str(tmp_path / "sol.raw")
-    assert tlinear.main(["--replay", prefix, "--solver", "conjugate_cuda", "--sol_out", sol]) == 0
-    out = capsys.readouterr().out
-    assert "iter=%d" % itg in out
-    x = np.fromfile(sol, dtype=np.float64).reshape(32, 32, 32)
-    assert rel_max_abs(x, xg) <= 1e-12   # same library, same inputs

@@ -473,101 +473,3 @@ def test_batched_x_update_is_bitwise_the_per_iteration_update(gpu, monkeypatch):
                 assert info.iter == maxiter + 1
                 out.append(x)
         assert np.array_equal(out[0], out[2]) and np.array_equal(out[1], out[3]), maxiter
-
-
-@pytest.mark.parametrize("shape", [(4, 16, 1024), (4, 1024, 128), (132, 8, 516)])
-def test_wide_meshes_with_walls(gpu, shape):
-    """rows / planes wider than one CTA's reach of every kernel (nx = 1024 is the x extent of
-    the 8-GPU weak-scaling domain), Neumann walls, variable density, against the oracle.
-    Six iterations only: these thin bars are so ill-conditioned that after 21 iterations a
-    1e-16 relative perturbation of the right-hand side moves the reference's own x by 8e-5
-    (and its block size by 6e-5); after six the reference is reproducible to 1e-13."""
-    case = case_density(None, nspheres=5, seed=11, rho_in=0.1, shape=shape)
-    conf = Conf(tol=0.0, miniter=0, maxiter=5)
-    x, info, hist = gpu_solve(case, conf)
-    xo, it_o, res_o, hist_o = oracle_solve(case, tol=0.0, miniter=0, maxiter=5)
-    assert info.iter == it_o == 6
-    np.testing.assert_allclose(hist, hist_o, rtol=1e-9)
-    assert rel_max_abs(x, xo) <= X_TOL
-
-
-@pytest.mark.skipif(__import__("os").environ.get("APHCG_TEST_DEFER") != "1",
-                    reason="opt-in kernel variant written after the round's GPU budget ended and "
-                           "never run on a GPU yet: run with APHCG_TEST_DEFER=1 (the default "
-                           "kernels' SASS is unchanged by it)")
-def test_deferred_consumption_variant_is_bitwise_identical(gpu, monkeypatch):
-    """APHCG_DEFER=1: the symmetric-storage direction kernel with the consumers of the
-    coefficient loads (lane shuffle for x+, y-/z- aliases) moved behind the plane barrier
-    (DESIGN.md section 8, item 1).  Same values into the same FMAs -> same bits, on meshes that
-    exercise every source of x+ (next lane, next warp, next CTA, last cell of the row), partial
-    tiles, walls and periodic wrap."""
-    cases = [case_tlinear(32), case_density(32, rho_in=0.01), case_tlinear(None, shape=(9, 16, 258)),
-             case_density(None, nspheres=5, seed=11, rho_in=0.1, shape=(4, 16, 1024)),
-             case_tlinear(None, shape=(1, 40, 40)), case_density(None, shape=(33, 8, 64), rho_in=0.1)]
-    for case in cases:
-        out = []
-        for flag in ("0", "1"):
-            monkeypatch.setenv("APHCG_DEFER", flag)
-            shape = case["system"].shape[:3]
-            solver = SolverConjugateCuda(Conf(tol=0.0, miniter=0, maxiter=40), {},
-                                         Mesh(shape=shape, periodic=case["periodic"]))
-            x = np.zeros(shape)
-            info = solver.Solve(case["system"], None, x)
-            desc = solver.Describe()
-            hist = solver.History(info.iter)
-            solver.close()
-            assert ("defer=1" in desc) == (flag == "1" and "sym4" in desc), desc
-            out.append((x, hist))
-        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), shape
-
-
-def test_device_resident_inputs_and_outputs(gpu):
-    """aphcg_set_system_device / aphcg_set_guess_device / aphcg_get_solution_device: rows, guess
-    and solution as DEVICE pointers (what a caller that assembles on the GPU would pass), compact
-    and laid out like a reference field with halos; same bits as the host-buffer path"""
-    import ctypes
-    import torch
-    case = case_density(24, rho_in=0.1)
-    shape = case["system"].shape[:3]
-    n, hl = 24, 2
-    x0 = random_guess(shape)
-    conf = Conf(tol=0.0, miniter=0, maxiter=30)
-    m = Mesh(shape=shape, periodic=case["periodic"])
-    x_host, info_host, _ = gpu_solve(case, conf, x0=x0)
-    L = capi.lib()
-    dev = torch.device("cuda", 0)
-    for padded in (False, True):
-        solver = SolverConjugateCuda(conf, {}, m)
-        if padded:
-            full = n + 2 * hl + 1
-            sys_full = np.full((full, full, full, 8), np.nan)
-            sys_full[hl:hl + n, hl:hl + n, hl:hl + n] = case["system"]
-            g_full = np.full((full, full, full), np.nan)
-            g_full[hl:hl + n, hl:hl + n, hl:hl + n] = x0
-            off = hl * (1 + full + full * full)
-            lay = capi.Layout(off, full, full * full)
-            d_sys, d_x0 = torch.from_numpy(sys_full).to(dev), torch.from_numpy(g_full).to(dev)
-            d_x = torch.full((full, full, full), 777.0, dtype=torch.float64, device=dev)
-            pl = ctypes.byref(lay)
-        else:
-            d_sys = torch.from_numpy(np.ascontiguousarray(case["system"])).to(dev)
-            d_x0 = torch.from_numpy(x0).to(dev)
-            d_x = torch.zeros(shape, dtype=torch.float64, device=dev)
-            pl = None
-        torch.cuda.synchronize()   # the library works on its own stream
-        assert L.aphcg_stream(solver._h), "the handle's cudaStream_t, for callers timing with events"
-        capi.check(L.aphcg_set_system_device(solver._h, ctypes.c_void_p(d_sys.data_ptr()), pl))
-        capi.check(L.aphcg_set_guess_device(solver._h, ctypes.c_void_p(d_x0.data_ptr()), pl))
-        info = solver.Run()
-        capi.check(L.aphcg_get_solution_device(solver._h, ctypes.c_void_p(d_x.data_ptr()), pl))
-        solver.close()
-        out = d_x.cpu().numpy()
-        if padded:
-            inner = out[hl:hl + n, hl:hl + n, hl:hl + n]
-            mask = np.ones_like(out, dtype=bool)
-            mask[hl:hl + n, hl:hl + n, hl:hl + n] = False
-            assert (out[mask] == 777.0).all(), "cells outside the inner block were touched"
-        else:
-            inner = out
-        assert info.iter == info_host.iter and info.residual == info_host.residual
-        assert np.array_equal(inner, x_host)
