@@ -408,6 +408,14 @@ def main_ours(args):
                           "achieved": B_ALG * cells * iters / (loop_ms * 1e-3) / 1e9,
                           "frac": B_ALG * cells * iters / (loop_ms * 1e-3) / 1e9 / peak},
         }
+    elif rank == 0:
+        # several GPUs: the kernels cannot be timed one by one (the peers would wait), so the
+        # roofline entry is the whole iteration, per GPU, against the same measured peak
+        peak, peak_src = peak_hbm_gbs()
+        ach = B_ALG * cells * iters / (loop_ms * 1e-3) / 1e9 / world
+        roofline = {"bound": "hbm", "kernel": "whole CG iteration, per GPU (k_dir_spmv + k_update + hand-offs)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "algorithmic_bytes_per_cell": B_ALG, "peak_source": peak_src}
 
     # ---- end to end: host buffers in, host buffer out, through aphcg_solve -----------
     e2e = None
