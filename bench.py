@@ -370,6 +370,8 @@ def main_ours(args):
         iters += info.iter
         loop_ms += info.loop_ms
     dev_ms = solver.TimerStop()
+    if args.steps < 1:
+        raise SystemExit("bench: --steps must be at least 1")
     if not (np.isfinite(info.residual) and np.isfinite(info.residual0) and info.residual0 > 0):
         raise SystemExit("bench: non-finite residual (%r, initial %r): the step did not compute"
                          % (info.residual, info.residual0))
