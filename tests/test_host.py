@@ -73,6 +73,32 @@ def test_group_argument_checks_and_partition(built):
         mod.Make(var, "symm", Mesh(shape=(64, 8, 8)))
 
 
+@pytest.mark.parametrize("world", [1, 2])
+def test_bench_line_contract_with_stubbed_solver(world):
+    """bench.py's JSON line (the driver's contract) assembled with the CUDA solver, torch.cuda
+    and torch.distributed stubbed out: every required key, at N = 1 and N > 1"""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "helpers", "bench_stub.py"),
+                          str(world)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "clocks",
+                "e2e", "gpu_launches", "roofline", "residual"):
+        assert key in line, key
+    assert line["n_gpus"] == world and line["dtype"] == "f64" and line["vs_baseline"] is None
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
+    if world == 1:
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
+        assert line["roofline"]["traffic"] and line["roofline"]["dram"]["frac"] < 1.0
+        assert abs(line["roofline"]["frac"] - 120.0 * 512 ** 3 / 1.89e-3 / 1e9 / line["roofline"]["peak"]) < 1e-9
+    else:
+        assert "cpu_baseline" not in line
+
+
 def test_group_sync_barrier(tmp_path):
     """the thread barrier / host all-reduce of the in-process slab group (cg_group.h)"""
     exe = str(tmp_path / "group_sync_test")
