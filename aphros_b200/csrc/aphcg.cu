@@ -61,7 +61,8 @@ struct IpcBlob {  // <= APHCG_IPC_BYTES
   int64_t ptotal, pz, poff, nzl;
   int32_t rank, pid;
   uint64_t base;  // device pointer (valid in the exporting process only)
-  int32_t device, pad;
+  int32_t device;   // ordinal in the exporting process
+  int32_t pci;      // PCI domain/bus/device of the GPU: the same for every process that uses it
 };
 static_assert(sizeof(IpcBlob) <= APHCG_IPC_BYTES, "blob too large");
 static_assert(sizeof(ncclUniqueId) <= APHCG_UNIQUE_ID_BYTES, "id too large");
@@ -123,6 +124,7 @@ struct aphcg {
   double* peer[kMaxRanks] = {};        // every rank's slab (own pointer for this rank)
   bool peer_opened[kMaxRanks] = {};
   bool use_mail = true;                // scalar all-reduce through peer mailboxes (else NCCL)
+  bool wait_in_kernel = false;         // Comm::wait_in_kernel (decided in aphcg_ipc_connect)
   bool connected = false;
   unsigned long long runs = 0;
   int64_t launches = 0;
@@ -199,14 +201,14 @@ int EnqueueIteration(aphcg_t* h) {
   } else {
     launch_dir_spmv_plain(h->g, h->d, h->vx, h->single, h->stream);
   }
-  if (!h->single) {
+  if (!h->single && !h->wait_in_kernel) {
     if (!h->use_mail) {
       if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
     }
     launch_finish_dir(h->d, h->stream);  // with mailboxes: waits for all ranks' partials
   }
   launch_update(h->g, h->d, h->vx, h->single, h->precond, h->stream);
-  if (!h->single) {
+  if (!h->single && !h->wait_in_kernel) {
     if (!h->use_mail) {
       if (int rc = AllReduce(h, &h->st->loc_sum, ncclSum)) return rc;
       if (h->precond) {
@@ -232,15 +234,24 @@ int EnqueueJacobiIteration(aphcg_t* h) {
   return 0;
 }
 
-int LaunchesPerIter(const aphcg_t* h) { return h->single ? 2 : 4; }
+int LaunchesPerIter(const aphcg_t* h) { return (h->single || h->wait_in_kernel) ? 2 : 4; }
+
+// ChunkIters() iterations: what the host enqueues (or replays as one graph) between two looks
+// at the exit flag.  With Comm::wait_in_kernel the update stage of the chunk's last iteration
+// is still pending at its end; one k_finish_upd folds it so that the host reads a committed
+// state (iteration count, residual, exit flag).
+int EnqueueChunk(aphcg_t* h, bool jacobi) {
+  for (int i = 0; i < ChunkIters(); ++i) {
+    if (int rc = jacobi ? EnqueueJacobiIteration(h) : EnqueueIteration(h)) return rc;
+  }
+  if (!jacobi && h->wait_in_kernel) launch_finish_upd(h->d, h->stream);
+  return 0;
+}
 
 int BuildGraph(aphcg_t* h, bool jacobi, cudaGraphExec_t* out) {
   cudaGraph_t graph = nullptr;
   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-  int rc = 0;
-  for (int i = 0; i < ChunkIters() && rc == 0; ++i) {
-    rc = jacobi ? EnqueueJacobiIteration(h) : EnqueueIteration(h);
-  }
+  const int rc = EnqueueChunk(h, jacobi);
   cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
   if (rc) {
     if (graph) cudaGraphDestroy(graph);
@@ -392,8 +403,12 @@ int WriteState(aphcg_t* h, const aphcg_conf* conf) {
   return 0;
 }
 
+// The residual history keeps the first kHistoryMax iterations at most (writes are bounded by
+// hist_cap on the device): a tolerance-driven Conf with a huge maxiter must not turn into a
+// multi-GB allocation, and growing is rare because a reallocation invalidates the graphs.
+constexpr int64_t kHistoryMax = 1 << 16;
 int EnsureHistory(aphcg_t* h, int maxiter) {
-  const int need = std::max(maxiter + 2, 16);
+  const int need = (int)std::min<int64_t>(std::max<int64_t>((int64_t)maxiter + 2, 16), kHistoryMax);
   if (need > h->hist_cap) {
     CK(cudaStreamSynchronize(h->stream));
     if (h->history) CK(cudaFree(h->history));
@@ -418,9 +433,7 @@ int RunLoop(aphcg_t* h, bool jacobi, const aphcg_conf* conf) {
     if (h->use_graph) {
       CK(cudaGraphLaunch(*gx, h->stream));
     } else {
-      for (int i = 0; i < ChunkIters(); ++i) {
-        if (int rc = jacobi ? EnqueueJacobiIteration(h) : EnqueueIteration(h)) return rc;
-      }
+      if (int rc = EnqueueChunk(h, jacobi)) return rc;
     }
     enq += ChunkIters();
     // poll the exit flag only when it can have fired: always with a tolerance,
@@ -434,6 +447,7 @@ int RunLoop(aphcg_t* h, bool jacobi, const aphcg_conf* conf) {
     }
   }
   h->launches += (int64_t)h->h_st->iter * (jacobi ? (h->single ? 1 : 2) : LaunchesPerIter(h));
+  if (!jacobi && h->wait_in_kernel) h->launches += (h->h_st->iter + ChunkIters() - 1) / ChunkIters();
   return 0;
 }
 
@@ -575,7 +589,7 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
     CKC(cudaMalloc(&h->rc, nb));
     h->d.rc = h->rc;
   }
-  h->hist_cap = 128;
+  h->hist_cap = 1024;
   CKC(cudaMalloc(&h->history, sizeof(double) * h->hist_cap));
   h->d.history = h->history;
   CKC(cudaDeviceSynchronize());
@@ -766,6 +780,10 @@ int aphcg_run_jacobi(aphcg_t* h, const aphcg_conf* conf, aphcg_info* info) {
   // iterate starts in p[0] (parity of iter = 0): copy the padded guess over
   CK(cudaMemcpyAsync(h->d.p[0], h->d.p[1], sizeof(double) * (size_t)h->g.ptotal,
                      cudaMemcpyDeviceToDevice, h->stream));
+  // Iteration 0 of a NEIGHBOUR stores its new boundary plane into this slab's p[1] ghost
+  // plane, which the copy above still reads: nobody starts iterating before every slab's
+  // copy is done.
+  if (int rc = StreamBarrier(h)) return rc;
   CK(cudaEventRecord(h->ev[1], h->stream));
   if (int rc = RunLoop(h, true, conf)) return rc;
   // result: inner cells of the current iterate -> compact u
@@ -839,10 +857,36 @@ int aphcg_apply(aphcg_t* h, const double* v, const aphcg_layout* v_layout, doubl
   launch_apply(h->g, h->d, h->vx, h->stream);
   h->launches += 2;
   CK(cudaGetLastError());
+  // the neighbours must not scatter their next field into this slab's ghost planes while
+  // the operator above still reads them
+  if (int rc = StreamBarrier(h)) return rc;
   if (int rc = CopyPlanes(h, out, h->ap, lo, false, 0, h->g.nzl, 8, cudaMemcpyDeviceToHost,
                           h->stream))
     return rc;
   CK(cudaStreamSynchronize(h->stream));
+  h->have_guess = false;
+  return 0;
+}
+
+int aphcg_true_residual(aphcg_t* h, double* sum_r2) {
+  if (!h || !sum_r2) return Fail(APHCG_ERR_ARG, "null argument");
+  if (!h->have_system) return Fail(APHCG_ERR_STATE, "no system uploaded");
+  if (!h->single && (!(h->comm || h->gs) || !h->connected))
+    return Fail(APHCG_ERR_STATE, "nranks > 1 needs aphcg_comm_init and aphcg_ipc_connect first");
+  if (int rc = SetDevice(h)) return rc;
+  // x -> padded field (+ the neighbours' ghost planes), then the stage-"init" kernel
+  // (linear.ipp:48-56) on it; its local sum r^2 lands in loc_sum2
+  launch_scatter_field(h->g, h->u, 0, h->g.cy, h->g.cz, nullptr, h->d.p[1], h->d.p_lo_dst[1],
+                       h->d.p_hi_dst[1], h->vx, h->stream);
+  if (int rc = StreamBarrier(h)) return rc;
+  launch_init_residual(h->g, h->d, h->vx, h->single, h->precond, h->stream);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->h_st, h->st, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *sum_r2 = h->h_st->loc_sum2;
+  // the neighbours must be done with this slab's ghost planes before anything else lands there
+  if (int rc = StreamBarrier(h)) return rc;
   h->have_guess = false;
   return 0;
 }
@@ -964,6 +1008,13 @@ int aphcg_ipc_export(aphcg_t* h, void* blob_out) {
   b.pid = (int32_t)getpid();
   b.base = (uint64_t)(uintptr_t)h->slab;
   b.device = h->desc.device;
+  {
+    int dom = 0, bus = 0, dev = 0;
+    CK(cudaDeviceGetAttribute(&dom, cudaDevAttrPciDomainId, h->desc.device));
+    CK(cudaDeviceGetAttribute(&bus, cudaDevAttrPciBusId, h->desc.device));
+    CK(cudaDeviceGetAttribute(&dev, cudaDevAttrPciDeviceId, h->desc.device));
+    b.pci = (dom << 16) | (bus << 8) | dev;
+  }
   memset(blob_out, 0, APHCG_IPC_BYTES);
   memcpy(blob_out, &b, sizeof(b));
   return 0;
@@ -1033,6 +1084,23 @@ int aphcg_ipc_connect(aphcg_t* h, const void* blobs, int32_t count) {
   d.cm.rank = me;
   d.cm.nranks = n;
   d.cm.use_mail = h->use_mail ? 1 : 0;
+  // Who waits for the all-reduced scalars: the consumer kernels' own CTAs (two launches per
+  // iteration), unless the reduction is NCCL's or two slabs share a GPU -- a grid of
+  // spinning CTAs would then keep the other slab's producer kernel off the SMs for good.
+  bool shared_gpu = false;
+  for (int q = 0; q < n; ++q)
+    for (int w = q + 1; w < n; ++w) shared_gpu |= (b[q].pci == b[w].pci);
+  h->wait_in_kernel = h->use_mail && !shared_gpu;
+  if (const char* ew = getenv("APHCG_WAIT")) {
+    if (!strcmp(ew, "finish")) h->wait_in_kernel = false;
+    if (!strcmp(ew, "kernel") && h->use_mail && !shared_gpu) h->wait_in_kernel = true;
+  }
+  d.cm.wait_in_kernel = h->wait_in_kernel ? 1 : 0;
+  {
+    const char* et = getenv("APHCG_MAIL_TIMEOUT_MS");
+    const double ms = et ? atof(et) : 20000.0;
+    d.cm.timeout_ns = (unsigned long long)((ms > 1.0 ? ms : 1.0) * 1e6);
+  }
   h->connected = true;
   InvalidateGraphs(h);
   return 0;
@@ -1122,7 +1190,10 @@ int aphcg_describe(aphcg_t* h, char* buf, int32_t buflen) {
   snprintf(buf, buflen, "spmv=%s%s %s precond=%s graph=%d allreduce=%s", h->use_tma ? "tma" : "plain",
            h->use_tma ? (h->sym ? "-sym4" : "-gen7") : "", t, h->precond ? "jacobi" : "none",
            h->use_graph ? 1 : 0,
-           h->single ? "none" : (h->use_mail ? "peer-mailbox" : "nccl"));
+           h->single ? "none"
+                     : (h->use_mail ? (h->wait_in_kernel ? "peer-mailbox/in-kernel-wait"
+                                                         : "peer-mailbox/finish-kernels")
+                                    : "nccl"));
   return 0;
 }
 

@@ -9,7 +9,11 @@
 // process-per-GPU mode would.  Inside the loop nothing changes (halo planes and the
 // scalars travel through peer memory, written by the kernels); outside it the two
 // collective steps of a solve use a thread barrier (cg_group.h) instead of NCCL.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <functional>
@@ -97,6 +101,56 @@ aphcg_layout SlabLayout(const aphcg_group* g, const aphcg_layout* l, int q) {
   return out;
 }
 
+// Slabs that share a GPU (a device ordinal repeats: the single-GPU test configuration,
+// `cuda_slabs_per_device` in the adapter) hand their scalars to each other through one-warp
+// kernels that spin on a mailbox, so the slabs' streams must sit on different hardware queues:
+// the driver has 8 by default and reads CUDA_DEVICE_MAX_CONNECTIONS when it creates the
+// device's context.  Raise it while that is still possible, refuse with a clear message when
+// it is not -- a deadlock on the GPU is the alternative.
+int EnsureConnections(const int32_t* devices, int n) {
+  int worst = 1, worst_dev = -1;
+  for (int q = 0; q < n; ++q) {
+    int rep = 0;
+    for (int w = 0; w < n; ++w) rep += (devices[w] == devices[q]);
+    if (rep > worst) {
+      worst = rep;
+      worst_dev = devices[q];
+    }
+  }
+  if (worst == 1) return 0;
+  const int need = 32;  // the driver's maximum; streams are spread over the queues
+  const char* e = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+  if (e && atoi(e) >= need) return 0;
+  // is the device's primary context already there?
+  using GetStateFn = CUresult (*)(CUdevice, unsigned int*, int*);
+  GetStateFn get_state = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  int active = 1;  // unknown counts as active
+  if (cudaGetDriverEntryPoint("cuDevicePrimaryCtxGetState", (void**)&get_state, cudaEnableDefault,
+                              &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess && get_state) {
+    unsigned flags = 0;
+    active = 0;
+    for (int q = 0; q < n; ++q) {
+      int a = 1;
+      if (get_state((CUdevice)devices[q], &flags, &a) != CUDA_SUCCESS) a = 1;
+      active |= a;
+    }
+  } else {
+    cudaGetLastError();
+  }
+  if (!active) {
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 1);
+    return 0;
+  }
+  return GroupFail(APHCG_ERR_STATE,
+                   std::to_string(worst) + " slabs share device " + std::to_string(worst_dev) +
+                       ": this needs CUDA_DEVICE_MAX_CONNECTIONS=32 in the environment before "
+                       "the process first touches the GPU (now: " +
+                       (e ? std::string(e) : std::string("unset")) +
+                       ", and the CUDA context already exists)");
+}
+
 void MergeInfo(const std::vector<aphcg_info>& v, aphcg_info* info) {
   if (!info) return;
   *info = v[0];  // residual and iter are bitwise the same on every slab
@@ -119,6 +173,7 @@ int aphcg_group_create(aphcg_group_t** out, const aphcg_desc* desc, const int32_
   if (desc->nz < ndevices)
     return GroupFail(APHCG_ERR_ARG, "cannot cut " + std::to_string(desc->nz) + " planes into " +
                                         std::to_string(ndevices) + " slabs");
+  if (int rc = EnsureConnections(devices, ndevices)) return rc;
   aphcg_group* g = new aphcg_group();
   g->n = ndevices;
   g->desc = *desc;
@@ -245,6 +300,16 @@ int aphcg_group_assemble_spheres(aphcg_group_t* g, const double* spheres, int32_
   return RunAll(g, [&](int q) {
     return aphcg_assemble_spheres(g->h[q], spheres, nspheres, rho_in, rho_out, dt);
   });
+}
+
+int aphcg_group_true_residual(aphcg_group_t* g, double* sum_r2) {
+  if (!g || !sum_r2) return GroupFail(APHCG_ERR_ARG, "null argument");
+  std::vector<double> v(g->n, 0.0);
+  if (int rc = RunAll(g, [&](int q) { return aphcg_true_residual(g->h[q], &v[q]); })) return rc;
+  double s = 0.0;
+  for (double x : v) s += x;
+  *sum_r2 = s;
+  return 0;
 }
 
 }  // extern "C"

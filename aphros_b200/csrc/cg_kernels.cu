@@ -78,18 +78,20 @@ __global__ void __launch_bounds__(kBX* kBY)
     k_dir_spmv_plain(const Geom g, const DevPtrs d) {
   __shared__ double sm[32];
   __shared__ int sm_flag;
+  __shared__ DirView view;
   CgState* st = d.st;
   if (st->done) return;
-  const double beta = cg_beta(st);
-  const double alpha_prev = st->alpha_prev;
-  const int par = st->iter & 1;
+  dir_view(d, &view);
+  const double beta = view.beta;
+  const double alpha_prev = view.alpha_prev;
+  const int par = view.iter & 1;
   const double* __restrict__ po = d.p[par];
   double* __restrict__ pn = d.p[par ^ 1];
   const double* __restrict__ r = d.r;
 
   const Tile t = my_tile<VX>(g);
   double acc = 0.0;
-  if (t.active) {
+  if (t.active && !view.done) {
     for (int k = t.k0; k < t.k1; ++k) {
       const int64_t idc = t.i + t.j * g.cy + k * g.cz;
       const int64_t idp = g.poff + t.i + t.j * g.py + k * g.pz;
@@ -150,11 +152,7 @@ __global__ void __launch_bounds__(kBX* kBY)
   if (tid == 0) d.partials[block_id()] = bsum;
   if (last_block(&st->counter_a, num_blocks(), &sm_flag)) {
     const double tot = reduce_slots<false>(d.partials, num_blocks(), sm);
-    if (tid == 0) {
-      st->loc_sum = tot;
-      if (kSingle) cg_finish_dir(st, tot);
-    }
-    if (!kSingle && d.cm.use_mail) mail_push(d.cm, st, 0, tot, 0.0);
+    dir_epilogue<kSingle>(d, view, tot);
   }
 }
 
@@ -175,9 +173,11 @@ template <int VX, bool kSingle, int UR, bool kPre>
 __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
   __shared__ double sm[32];
   __shared__ int sm_flag;
+  __shared__ UpdView view;
   CgState* st = d.st;
   if (st->done) return;
-  const double alpha = cg_alpha(st);
+  upd_view(d, &view);
+  const double alpha = view.alpha;
   double* __restrict__ r = d.r;
   double acc2 = 0.0;
   // g.utx threads span one row segment; on narrow meshes (nx/VX < kUT) the remaining
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
   const int tx = threadIdx.x % utx, ty = threadIdx.x / utx;
   const int xchunks = (g.nx + utx * VX - 1) / (utx * VX);
   const int jgroups = (g.ny + UR * uty - 1) / (UR * uty);
-  const int64_t nwork = (int64_t)xchunks * jgroups * g.nzl;
+  const int64_t nwork = view.error ? 0 : (int64_t)xchunks * jgroups * g.nzl;
   double acc = 0.0, amax = 0.0;
   for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
     const int xc = (int)(w % xchunks);
@@ -258,9 +258,16 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
       st->loc_sum = tot;
       st->loc_max = mx;
       st->loc_sum2 = tot2;
+      if (view.pend) cg_finish_dir(st, view.pAp);  // every CTA has read the old state by now
+      if (view.error) {
+        st->error = 1;
+        st->done = 1;
+      }
       if (kSingle) cg_finish_upd(st, d.history, tot, mx, tot2);
+      if (!kSingle && d.cm.wait_in_kernel && !view.error) st->pend_upd = 1;
     }
-    if (!kSingle && d.cm.use_mail) mail_push(d.cm, st, 1, tot, mx, tot2);
+    if (!kSingle && d.cm.use_mail && !view.error)
+      mail_push(d.cm, st->seq_base, view.iter, 1, tot, mx, tot2);
   }
 }
 
@@ -312,14 +319,23 @@ __global__ void k_finish_dir(const DevPtrs d) {
   CgState* st = d.st;
   if (st->done) return;
   double sum = st->loc_sum, mx = 0.0, sum2 = 0.0;
-  if (d.cm.use_mail && !mail_wait(d.cm, st, 0, &sum, &mx, &sum2)) return;
+  if (d.cm.use_mail && !mail_wait(d.cm, st->seq_base, st->iter, 0, &sum, &mx, &sum2)) {
+    if (threadIdx.x == 0) st->error = st->done = 1;
+    return;
+  }
   if (threadIdx.x == 0) cg_finish_dir(st, sum);
 }
 __global__ void k_finish_upd(const DevPtrs d) {
   CgState* st = d.st;
   if (st->done) return;
+  // Comm::wait_in_kernel: runs once per chunk of iterations, so that the host finds a fully
+  // committed state when it looks; nothing to do unless an update stage is pending
+  if (d.cm.wait_in_kernel && !st->pend_upd) return;
   double sum = st->loc_sum, mx = st->loc_max, sum2 = st->precond ? st->loc_sum2 : st->loc_sum;
-  if (d.cm.use_mail && !mail_wait(d.cm, st, 1, &sum, &mx, &sum2)) return;
+  if (d.cm.use_mail && !mail_wait(d.cm, st->seq_base, st->iter, 1, &sum, &mx, &sum2)) {
+    if (threadIdx.x == 0) st->error = st->done = 1;
+    return;
+  }
   if (threadIdx.x == 0) cg_finish_upd(st, d.history, sum, mx, st->precond ? sum2 : sum);
 }
 __global__ void k_finish_init(CgState* st) {
@@ -542,7 +558,10 @@ __global__ void k_finish_jacobi(const DevPtrs d) {
   CgState* st = d.st;
   if (st->done) return;
   double sum = 0.0, mx = st->loc_max, sum2 = 0.0;
-  if (d.cm.use_mail && !mail_wait(d.cm, st, 0, &sum, &mx, &sum2)) return;
+  if (d.cm.use_mail && !mail_wait(d.cm, st->seq_base, st->iter, 0, &sum, &mx, &sum2)) {
+    if (threadIdx.x == 0) st->error = st->done = 1;
+    return;
+  }
   if (threadIdx.x == 0) jacobi_finish(st, d.history, mx);
 }
 
@@ -598,7 +617,7 @@ __global__ void __launch_bounds__(kBX* kBY) k_jacobi(const Geom g, const DevPtrs
       st->loc_max = mx;
       if (kSingle) jacobi_finish(st, d.history, mx);
     }
-    if (!kSingle && d.cm.use_mail) mail_push(d.cm, st, 0, 0.0, mx);
+    if (!kSingle && d.cm.use_mail) mail_push(d.cm, st->seq_base, st->iter, 0, 0.0, mx);
   }
 }
 

@@ -111,36 +111,49 @@ __device__ __forceinline__ double reduce_slots(const double* slots, unsigned n, 
 
 // ---- peer-memory all-reduce (see cg_types.h) -------------------------------------
 // phase 0: p.Ap (after the direction kernel), phase 1: r.r / max|r| (after the update)
-__device__ __forceinline__ unsigned long long mail_seq(const CgState* st, int phase) {
-  return st->seq_base + 2ull * (unsigned long long)st->iter + (unsigned long long)phase + 1ull;
+__device__ __forceinline__ unsigned long long mail_seq(unsigned long long seq_base, int iter,
+                                                       int phase) {
+  return seq_base + 2ull * (unsigned long long)iter + (unsigned long long)phase + 1ull;
 }
-// Called by every thread of the CTA that finished the local reduction.
-__device__ __forceinline__ void mail_push(const Comm& cm, const CgState* st, int phase, double sum,
-                                          double mx, double sum2 = 0.0) {
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Called by every thread of the CTA that finished the local reduction of iteration `iter`.
+__device__ __forceinline__ void mail_push(const Comm& cm, unsigned long long seq_base, int iter,
+                                          int phase, double sum, double mx, double sum2 = 0.0) {
   const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
   if (tid < cm.nranks) {
-    MailSlot* s = cm.box[tid] + ((phase * 2 + (st->iter & 1)) * kMaxRanks + cm.rank);
+    MailSlot* s = cm.box[tid] + ((phase * 2 + (iter & 1)) * kMaxRanks + cm.rank);
     *reinterpret_cast<volatile double*>(&s->sum) = sum;
     *reinterpret_cast<volatile double*>(&s->mx) = mx;
     *reinterpret_cast<volatile double*>(&s->sum2) = sum2;
     __threadfence_system();  // values (and this kernel's halo stores) before the flag
-    *reinterpret_cast<volatile unsigned long long*>(&s->seq) = mail_seq(st, phase);
+    *reinterpret_cast<volatile unsigned long long*>(&s->seq) = mail_seq(seq_base, iter, phase);
   }
 }
-// Called by one warp.  Returns false (and flags the error) on timeout.
-__device__ __forceinline__ bool mail_wait(const Comm& cm, CgState* st, int phase, double* sum,
-                                          double* mx, double* sum2) {
+// Called by one full warp.  Waits for every rank's contribution of (iter, phase) in the LOCAL
+// mailbox and adds them in rank order.  Returns false on timeout (a peer died or never ran:
+// the wall-clock limit cm.timeout_ns keeps the GPU from hanging).
+__device__ __forceinline__ bool mail_wait(const Comm& cm, unsigned long long seq_base, int iter,
+                                          int phase, double* sum, double* mx, double* sum2) {
   const int lane = threadIdx.x & 31;
-  const unsigned long long want = mail_seq(st, phase);
+  const unsigned long long want = mail_seq(seq_base, iter, phase);
   double vs = 0.0, vm = 0.0, v2 = 0.0;
   bool ok = true;
   if (lane < cm.nranks) {
-    MailSlot* s = cm.box[cm.rank] + ((phase * 2 + (st->iter & 1)) * kMaxRanks + lane);
-    const long long t0 = clock64();
+    MailSlot* s = cm.box[cm.rank] + ((phase * 2 + (iter & 1)) * kMaxRanks + lane);
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
     while (*reinterpret_cast<volatile unsigned long long*>(&s->seq) != want) {
-      if (clock64() - t0 > 8000000000ll) {  // ~4 s: a peer died; do not hang the GPU
-        ok = false;
-        break;
+      if ((++spins & 1023u) == 0) {
+        const unsigned long long now = global_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > cm.timeout_ns) {
+          ok = false;
+          break;
+        }
       }
     }
     __threadfence_system();
@@ -158,10 +171,6 @@ __device__ __forceinline__ bool mail_wait(const Comm& cm, CgState* st, int phase
   *sum = ts;
   *mx = tm;
   *sum2 = t2;
-  if (!ok && lane == 0) {
-    st->error = 1;
-    st->done = 1;
-  }
   return ok;
 }
 
@@ -174,26 +183,148 @@ __device__ __forceinline__ double cg_beta(const CgState* st) {
 }
 
 // after the direction/SpMV kernel: global p.Ap is known
-__device__ __forceinline__ void cg_finish_dir(CgState* st, double pap) { st->pAp = pap; }
+__device__ __forceinline__ void cg_finish_dir(CgState* st, double pap) {
+  st->pAp = pap;
+  st->pend_dir = 0;
+}
 
-// after the update kernel: global sum r^2 and max|r| are known.
-// Advances the iteration and evaluates the exit rule (linear.ipp:102-113).
+// What the end of the update stage does to the loop scalars (linear.ipp:83-114): computed as
+// a value so that a kernel can look one stage ahead without writing the shared state.
 // rr_new: numerator of the next alpha/beta (sum r^2, or sum r.z when preconditioned);
 // rnorm2: sum r^2, the residual norm.
+struct CgStep {
+  double alpha_prev, alpha_prev2, rr, rr_prev, rnorm2, max_r, residual;
+  int iter, done;
+};
+__device__ __forceinline__ CgStep cg_step(const CgState* st, double rr_new, double max_r,
+                                          double rnorm2) {
+  CgStep n;
+  n.alpha_prev2 = st->alpha_prev;
+  n.alpha_prev = cg_alpha(st);
+  n.rr_prev = st->rr;
+  n.rr = rr_new;
+  n.rnorm2 = rnorm2;
+  n.max_r = max_r;
+  n.residual = st->maxnorm ? max_r / st->cell_volume : sqrt(rnorm2 / st->cell_volume);
+  n.iter = st->iter + 1;
+  n.done = (n.iter >= st->miniter && (n.iter > st->maxiter || n.residual < st->tol)) ? 1 : 0;
+  return n;
+}
+__device__ __forceinline__ void cg_commit(CgState* st, double* history, const CgStep& n) {
+  st->alpha_prev2 = n.alpha_prev2;
+  st->alpha_prev = n.alpha_prev;
+  st->rr_prev = n.rr_prev;
+  st->rr = n.rr;
+  st->rnorm2 = n.rnorm2;
+  st->max_r = n.max_r;
+  st->residual = n.residual;
+  if (n.iter - 1 < st->hist_cap) history[n.iter - 1] = n.residual;
+  st->iter = n.iter;
+  st->pend_upd = 0;
+  if (n.done) st->done = 1;
+}
+// after the update kernel: global sum r^2 and max|r| are known.
+// Advances the iteration and evaluates the exit rule (linear.ipp:102-113).
 __device__ __forceinline__ void cg_finish_upd(CgState* st, double* history, double rr_new,
                                               double max_r, double rnorm2) {
-  st->alpha_prev2 = st->alpha_prev;
-  st->alpha_prev = cg_alpha(st);
-  st->rr_prev = st->rr;
-  st->rr = rr_new;
-  st->rnorm2 = rnorm2;
-  st->max_r = max_r;
-  const double res = st->maxnorm ? max_r / st->cell_volume : sqrt(rnorm2 / st->cell_volume);
-  st->residual = res;
-  const int it = st->iter + 1;
-  if (it - 1 < st->hist_cap) history[it - 1] = res;
-  st->iter = it;
-  if (it >= st->miniter && (it > st->maxiter || res < st->tol)) st->done = 1;
+  cg_commit(st, history, cg_step(st, rr_new, max_r, rnorm2));
+}
+
+// ---- the loop scalars as a consumer kernel sees them (Comm::wait_in_kernel) ------------
+// Direction kernel: beta, the alphas of the deferred x updates and the iteration number, with
+// the update stage of the previous iteration folded in when its all-reduce is still pending.
+struct DirView {
+  CgStep next;      // valid when pend
+  double beta, alpha_prev, alpha_prev2;
+  int iter, done, pend, error;
+};
+// All threads of the CTA call; `sv` is shared memory.  When the previous update stage is
+// pending, warp 0 waits for every rank's r.r / max|r| in the local mailbox; the fence chain
+// (peer's halo stores -> its ticket -> its mailbox flag -> this acquire) also makes the
+// neighbours' boundary planes of r visible before this CTA reads its ghost planes, through
+// TMA included (fence.proxy.async).
+__device__ __forceinline__ void dir_view(const DevPtrs& d, DirView* sv) {
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  if (tid < 32) {
+    const CgState* st = d.st;
+    DirView v;
+    v.pend = st->pend_upd;
+    v.error = 0;
+    if (!v.pend) {
+      v.iter = st->iter;
+      v.done = st->done;
+      v.beta = cg_beta(st);
+      v.alpha_prev = st->alpha_prev;
+      v.alpha_prev2 = st->alpha_prev2;
+    } else {
+      double sum, mx, sum2;
+      const bool ok = mail_wait(d.cm, st->seq_base, st->iter, 1, &sum, &mx, &sum2);
+      v.next = cg_step(st, sum, mx, st->precond ? sum2 : sum);
+      if (!ok) {
+        v.next.done = 1;
+        v.error = 1;
+      }
+      v.iter = v.next.iter;
+      v.done = v.next.done;
+      v.beta = v.next.rr / (v.next.rr_prev + 1e-100);  // iter >= 1 here (linear.ipp:98)
+      v.alpha_prev = v.next.alpha_prev;
+      v.alpha_prev2 = v.next.alpha_prev2;
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    if (tid == 0) *sv = v;
+  }
+  __syncthreads();
+}
+// Last CTA of the direction kernel, thread 0: commit what dir_view folded.
+__device__ __forceinline__ void dir_commit(const DevPtrs& d, const DirView& v) {
+  if (!v.pend) return;
+  cg_commit(d.st, d.history, v.next);
+  if (v.error) {
+    d.st->error = 1;
+    d.st->done = 1;
+  }
+}
+
+// Last CTA of a direction kernel, all threads: `tot` is this rank's sum p.Ap.
+template <bool kSingle>
+__device__ __forceinline__ void dir_epilogue(const DevPtrs& d, const DirView& v, double tot) {
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  CgState* st = d.st;
+  if (tid == 0) {
+    dir_commit(d, v);  // every CTA has read the old state by now (ticket)
+    if (!v.done) {
+      st->loc_sum = tot;
+      if (kSingle) cg_finish_dir(st, tot);
+      if (!kSingle && d.cm.wait_in_kernel) st->pend_dir = 1;
+    }
+  }
+  if (!kSingle && d.cm.use_mail && !v.done) mail_push(d.cm, st->seq_base, v.iter, 0, tot, 0.0);
+}
+
+// Update kernel: alpha, with the direction stage's p.Ap folded in when pending.
+struct UpdView {
+  double alpha, pAp;
+  int iter, pend, error;
+};
+__device__ __forceinline__ void upd_view(const DevPtrs& d, UpdView* sv) {
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  if (tid < 32) {
+    const CgState* st = d.st;
+    UpdView v;
+    v.pend = st->pend_dir;
+    v.iter = st->iter;
+    v.error = 0;
+    if (!v.pend) {
+      v.pAp = st->pAp;
+    } else {
+      double sum, mx, sum2;
+      if (!mail_wait(d.cm, st->seq_base, st->iter, 0, &sum, &mx, &sum2)) v.error = 1;
+      v.pAp = sum;
+    }
+    v.alpha = st->rr / (v.pAp + 1e-100);  // linear.ipp:84
+    if (tid == 0) *sv = v;
+  }
+  __syncthreads();
 }
 
 }  // namespace acg

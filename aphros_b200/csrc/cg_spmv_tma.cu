@@ -115,28 +115,34 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ double sm_red[32];
   __shared__ int sm_flag;
+  __shared__ DirView view;
   constexpr int BOXD = BOXB / 8;  // doubles per staged box (padded to 128 bytes)
   double* const smd = reinterpret_cast<double*>(smem_raw);
   // layout: [S x (r box | p_old box)] [RING x p_new box] [S mbarriers]
   uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + (2 * S + RING) * BOXB);
   CgState* st = d.st;
   if (st->done) return;
-  const double beta = cg_beta(st);
-  const double alpha_prev = st->alpha_prev, alpha_prev2 = st->alpha_prev2;
-  const int par = st->iter & 1;
+  // loop scalars; with several GPUs this is where the CTA waits for the all-reduced r.r of the
+  // previous update stage (and, by the same acquire, for the neighbours' boundary planes of r)
+  dir_view(d, &view);
+  const double beta = view.beta;
+  const double alpha_prev = view.alpha_prev, alpha_prev2 = view.alpha_prev2;
+  const int par = view.iter & 1;
   const CUtensorMap* map_po = par ? &map_p1 : &map_p0;
   // p_new goes where p_{k-2} lives; the batched x update reads it from there first
   double* pn_glob = d.p[par ^ 1];
   // deferred x updates applied by this launch (CgState::xbatch): 1 = the last one (every
   // iteration), 2 = the last two (even iterations), 0 = none (odd iterations; iteration 0)
-  const int xmode = !st->xbatch ? 1 : ((par || st->iter == 0) ? 0 : 2);
+  const int xmode = !st->xbatch ? 1 : ((par || view.iter == 0) ? 0 : 2);
 
   const int tid = threadIdx.x;
   const bool pstream = (opts & 1) != 0;  // streaming (evict-first) stores of p_new
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   const int k0 = blockIdx.z * zc;
   const int k1 = min(k0 + zc, g.nzl);
-  const int np = k1 - k0 + 2;  // planes k0-1 .. k1
+  // planes k0-1 .. k1; none when the folded exit rule has just fired (the last CTA still
+  // commits it below)
+  const int np = view.done ? 0 : k1 - k0 + 2;
 
   // TMA coordinates of the box origin (element units of the padded tensor)
   const int c0 = kGhostX + x0 - 2, c1 = y0;  // row index 1+(y0-1)
@@ -411,11 +417,7 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
   if (tid == 0) d.partials[bid] = bsum;
   if (last_block(&st->counter_a, nblk, &sm_flag)) {
     const double tot = reduce_slots<false>(d.partials, nblk, sm_red);
-    if (tid == 0) {
-      st->loc_sum = tot;
-      if (kSingle) cg_finish_dir(st, tot);
-    }
-    if (!kSingle && d.cm.use_mail) mail_push(d.cm, st, 0, tot, 0.0);
+    dir_epilogue<kSingle>(d, view, tot);
   }
 }
 

@@ -49,7 +49,13 @@ struct Comm {
   MailSlot* box[kMaxRanks];  // box[q]: rank q's slot array (own memory for q == rank)
   int rank, nranks;
   int use_mail;  // 1: mailboxes; 0: an NCCL all-reduce on loc_sum/loc_max follows the kernel
-  int pad;
+  // 1: the kernel that CONSUMES a reduced scalar waits for the mailboxes itself (every CTA of
+  //    k_update for p.Ap, every CTA of the direction kernel for r.r), so an iteration is two
+  //    launches on any number of GPUs; 0: one-warp k_finish_* kernels do the waiting (NCCL
+  //    reduction, or slabs that share one GPU: a grid of spinning CTAs would keep the peer
+  //    slab's producer kernel off the SMs)
+  int wait_in_kernel;
+  unsigned long long timeout_ns;  // a wait that sees nothing for this long flags APHCG_ERR_COMM
 };
 
 // Loop state; lives in device memory, updated by the kernels themselves so the
@@ -89,6 +95,10 @@ struct CgState {
                  // unchanged, but x is read and written every other iteration (p_{k-2} is
                  // still in the buffer p_k is about to overwrite): 12 instead of 16 B/cell
   unsigned long long seq_base;  // distinguishes the mailbox traffic of successive runs
+  // Comm::wait_in_kernel: this rank's partial result of the direction / update stage has been
+  // pushed, but the all-reduced value is not folded into the state above yet -- the consumer
+  // kernel's CTAs fold it for themselves and its last CTA commits it (cg_kernels.cuh)
+  int pend_dir, pend_upd;
 };
 
 struct DevPtrs {

@@ -208,6 +208,13 @@ class _CudaSolverBase(Solver):
         capi.check(capi.lib().aphcg_apply(self._h, capi.ptr(v), ctypes.byref(lv), capi.ptr(out), None))
         return out
 
+    def TrueResidualSum(self):
+        """this rank's sum r^2 with r = -(A x + e7) recomputed on the device from the
+        resident solution (collective when nranks > 1; the caller adds the ranks)"""
+        out = ctypes.c_double()
+        capi.check(capi.lib().aphcg_true_residual(self._h, ctypes.byref(out)))
+        return out.value
+
     def AssembleSpheres(self, spheres, rho_in=1e-3, rho_out=1.0, dt=1e-3):
         sph = np.ascontiguousarray(spheres, dtype=np.float64).reshape(-1, 4)
         capi.check(capi.lib().aphcg_assemble_spheres(self._h, capi.ptr(sph), sph.shape[0],
@@ -390,6 +397,12 @@ class _GroupSolverBase(_CudaSolverBase):
         sph = np.ascontiguousarray(spheres, dtype=np.float64).reshape(-1, 4)
         capi.check(capi.lib().aphcg_group_assemble_spheres(self._g, capi.ptr(sph), sph.shape[0],
                                                            rho_in, rho_out, dt))
+
+    def TrueResidualSum(self):
+        """sum r^2 over all slabs, r = -(A x + e7) recomputed from the resident solution"""
+        out = ctypes.c_double()
+        capi.check(capi.lib().aphcg_group_true_residual(self._g, ctypes.byref(out)))
+        return out.value
 
     def History(self, n=None):
         n = int(n if n is not None else self.conf.maxiter + 2)

@@ -147,6 +147,13 @@ int aphcg_run_jacobi(aphcg_t* h, const aphcg_conf* conf, aphcg_info* info);
 int aphcg_apply(aphcg_t* h, const double* v, const aphcg_layout* v_layout,
                 double* out, const aphcg_layout* out_layout);
 
+/* sum over this rank's cells of r^2, r = -(A x + e7) RECOMPUTED from the resident solution
+ * of the last run (the loop itself only carries the recursively updated residual, like
+ * linear.ipp:89,102-107).  With nranks > 1 it is a collective call (the neighbours' boundary
+ * planes of x are exchanged) and the caller adds the ranks' values.  For checking a converged
+ * solve at sizes where the solution cannot be compared on the host. */
+int aphcg_true_residual(aphcg_t* h, double* sum_r2);
+
 /* Synthetic variable-density projection system assembled on the device from a
  * sphere list (formulas of src/solver/proj.ipp:343-398):
  * spheres = nspheres x {cx,cy,cz,r}.  Replaces upload_system for benchmarks
@@ -226,6 +233,8 @@ int aphcg_group_download_solution(aphcg_group_t* g, double* x, const aphcg_layou
 int aphcg_group_assemble_spheres(
     aphcg_group_t* g, const double* spheres, int32_t nspheres, double rho_in, double rho_out,
     double dt);
+/* sum over ALL slabs (added in slab order) */
+int aphcg_group_true_residual(aphcg_group_t* g, double* sum_r2);
 
 /* Device-side timing on the handle's stream (CUDA events): start records an
  * event; stop records another, waits for it and returns the milliseconds between. */

@@ -130,9 +130,13 @@ def have_reference_dim2():
 
 def solve_reference(system, x0=None, *, periodic=(True, True, True), tol=0.0, miniter=0,
                     maxiter=100, maxnorm=False, block=None, solver="conjugate",
-                    plugin=None, threads=1, repeat=1, extra="", env=None, workdir=None, dim=3):
+                    plugin=None, threads=1, repeat=1, extra="", env=None, workdir=None, dim=3,
+                    binary=None):
     """Run the reference's own solver (oracle/_ref/ref_cg; dim=2: ref_cg2, a 2-D mesh,
     system shape (1, ny, nx, 8) whose z coefficients are ignored).
+
+    `binary`: another build of the same driver (oracle/_ref/ref_cg_native: the reference's
+    default -march=native flags, used for timing only).
 
     Returns (x, iter, residual, seconds).  Mesh extent is 1 (h = 1/max(n)).
     """
@@ -146,7 +150,7 @@ def solve_reference(system, x0=None, *, periodic=(True, True, True), tol=0.0, mi
     with tempfile.TemporaryDirectory(dir=workdir) as tmp:
         fsys = os.path.join(tmp, "sys.f64")
         system.tofile(fsys)
-        cmd = [REF_CG2 if dim == 2 else REF_CG, "--nx", str(nx), "--ny", str(ny), "--nz", str(nz),
+        cmd = [binary or (REF_CG2 if dim == 2 else REF_CG), "--nx", str(nx), "--ny", str(ny), "--nz", str(nz),
                "--bsx", str(b[0]), "--bsy", str(b[1]), "--bsz", str(b[2]),
                "--sys", fsys, "--out", os.path.join(tmp, "out"),
                "--tol", repr(float(tol)), "--maxiter", str(maxiter), "--miniter", str(miniter),

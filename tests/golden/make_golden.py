@@ -6,7 +6,17 @@ oracle/ref/Makefile).  Run in the build container (needs /root/reference):
 
 Each fixture stores the inputs' recipe (regenerated from seeds by
 aphros_b200.systems, checked by a checksum), the reference's iteration count,
-final residual and solution.  Small on purpose (<= 24^3).
+final residual and solution.  Small on purpose (<= 24^3), except
+
+    python tests/golden/make_golden.py large      (about 10 minutes, 8 cores, 12 GB)
+
+which adds
+  * bench_parity_64: a 64^3 variable-density system (10:1, walls) solved to 1e-10 x the
+    initial residual -- the system bench.py cuts into z-slabs at N > 1 for its untimed parity
+    check (iteration count, residual and the whole solution: 2 MB);
+  * config5_384_periodic: BASELINE.json config 5 ("384^3 periodic projection solve,
+    iterations-to-tolerance vs reference"): the reference's iteration count and residual at
+    tol = 1e-7 x initial residual, plus the solution at 4096 sample cells (not the 453 MB field).
 """
 
 import hashlib
@@ -57,6 +67,48 @@ def build_case(name):
     raise KeyError(name)
 
 
+def build_large(name):
+    if name == "bench_parity_64":
+        shape = (64, 64, 64)
+        s, _ = systems.density_poisson_system(None, nspheres=6, seed=4, rho_in=0.1, shape=shape)
+        tol = 1e-10 * float(np.sqrt((s[..., 7] ** 2).sum() / systems.cell_volume(shape)))
+        return s, None, (False, False, False), dict(tol=tol, maxiter=5000, block=16)
+    if name == "config5_384_periodic":
+        shape = (384, 384, 384)
+        s, _ = systems.periodic_constant_system(384)
+        tol = 1e-7 * float(np.sqrt((s[..., 7] ** 2).sum() / systems.cell_volume(shape)))
+        return s, None, (True, True, True), dict(tol=tol, maxiter=5000, block=32)
+    raise KeyError(name)
+
+
+def sample_index(shape, count=4096, seed=777):
+    """flat indices of the sample cells of a large fixture"""
+    return np.sort(np.random.default_rng(seed).choice(int(np.prod(shape)), count, replace=False))
+
+
+def main_large():
+    assert cpu.have_reference(), "build oracle/_ref first: make -C oracle/ref"
+    threads = os.cpu_count() or 1
+    workdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    for name in ["bench_parity_64", "config5_384_periodic"]:
+        s, x0, per, kw = build_large(name)
+        x, it, res, sec = cpu.solve_reference(s, x0, periodic=per, threads=threads, workdir=workdir,
+                                              **kw)
+        out = dict(iter=it, residual=res, tol=kw["tol"], block=kw["block"], threads=threads,
+                   seconds=sec)
+        if x.size <= 64 ** 3:
+            out["x"] = x
+            out["system_sha256"] = checksum(s)
+        else:
+            idx = sample_index(x.shape)
+            out["sample_index"] = idx
+            out["sample_x"] = x.reshape(-1)[idx]
+            out["x_mean"] = float(x.mean())
+            out["rhs_sha256"] = checksum(s[..., 7])
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, it, res, "%.1f s" % sec, flush=True)
+
+
 CASES = ["tlinear16_b8", "tlinear24_b12_guess", "tlinear_ragged", "density24_neumann",
          "density16_1000to1_fixed", "const20_periodic_maxnorm", "tlinear16_miniter",
          "tlinear16_jacobi"]
@@ -77,4 +129,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "large":
+        main_large()
+    else:
+        main()

@@ -59,6 +59,10 @@ bench.ClockSampler.stop = lambda self: {"sm_mhz": 1800.0, "sm_max_mhz": 1965.0,
                                         "reasons": ["sw_power_cap"], "samples": 5}
 bench.run_reference_cpu = lambda *a, **k: {"value": 3.9e8, "unit": bench.UNIT, "cores": 16,
                                            "kind": "reference", "sample": "stub"}
+bench.parity_check = lambda world, rank, local_rank, d: {
+    "rel_max_abs": 2e-13, "iter": 1730, "iter_reference": 1730, "ok": True}
+bench.strong_measurement = lambda args, world, rank, local_rank, d, barrier: {
+    "value": 9.0e10, "unit": bench.UNIT, "n1_value": 5.2e10, "efficiency_vs_n1": 9.0 / (world * 5.2)}
 capi.PinnedArray = type("PA", (), {"__init__": lambda self, shape: setattr(self, "array", np.zeros(2)),
                                    "free": lambda self: None})
 capi.lib = lambda: types.SimpleNamespace(aphcg_download_system=lambda *a: 0)

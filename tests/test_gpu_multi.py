@@ -63,9 +63,9 @@ for name in ["tlinear_periodic", "density_walls", "uneven"]:
     xbudget, spread = solution_budget(s, x0, per, tol, 3000, blocks=(4, 8, 16))
     good = (iterations_ok(info.iter, counts + [it_o]) and err <= xbudget and info2.iter == it_o2
             and (not stable or abs(info2.residual - res_o2) <= 1e-7 * res_o2))
-    print("rank %%d %%s: iter %%d/%%d err %%.2e | iter %%d/%%d res %%.6e/%%.6e %%s" %% (
+    print("rank %%d %%s: iter %%d/%%d err %%.2e | iter %%d/%%d res %%.6e/%%.6e %%s [%%s]" %% (
         rank, name, info.iter, it_o, err, info2.iter, it_o2, info2.residual, res_o2,
-        "OK" if good else "FAIL"), flush=True)
+        "OK" if good else "FAIL", solver.Describe().split("allreduce=")[-1]), flush=True)
     ok = ok and good
     solver.close()
 dist.barrier()
@@ -74,17 +74,21 @@ sys.exit(0 if ok else 1)
 """
 
 
-@pytest.mark.parametrize("world,allreduce", [(2, "mail"), (2, "nccl"), (4, "mail"), (8, "mail")])
+@pytest.mark.parametrize("world,allreduce", [(2, "mail"), (2, "mail-finish"), (2, "nccl"),
+                                             (4, "mail"), (8, "mail"), (8, "mail-finish")])
 def test_slabs_match_single_domain_oracle(gpu, tmp_path, world, allreduce):
-    """allreduce: "mail" = scalars through peer-memory mailboxes written by the kernels
-    (the product path); "nccl" = ncclAllReduce on the same stream (comparison path)"""
+    """allreduce: "mail" = scalars through peer-memory mailboxes written by the kernels and
+    awaited by the consumer kernels' own CTAs (the product path: two launches per iteration);
+    "mail-finish" = the same mailboxes awaited by one-warp k_finish_* kernels (what slabs that
+    share a GPU use); "nccl" = ncclAllReduce on the same stream (comparison path)"""
     if capi.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT})
     env = dict(os.environ, MASTER_ADDR="127.0.0.1",
-               MASTER_PORT=str(29600 + world + (50 if allreduce == "nccl" else 0)),
-               WORLD_SIZE=str(world), APHCG_ALLREDUCE=allreduce)
+               MASTER_PORT=str(29600 + world + {"mail": 0, "nccl": 50, "mail-finish": 100}[allreduce]),
+               WORLD_SIZE=str(world), APHCG_ALLREDUCE=allreduce.split("-")[0],
+               APHCG_WAIT="finish" if allreduce == "mail-finish" else "kernel")
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
              for r in range(world)]
@@ -98,3 +102,4 @@ def test_slabs_match_single_domain_oracle(gpu, tmp_path, world, allreduce):
             pytest.fail("multi-GPU worker timed out")
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, "rank %d failed:\n%s" % (r, o[-3000:])
+    print("".join(o for o in outs[:1]))  # rank 0's lines, for the saved logs (pytest -s / -rP)

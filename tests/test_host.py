@@ -91,9 +91,14 @@ def test_bench_line_contract_with_stubbed_solver(world):
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
+    assert {"rel_max_abs", "iter", "iter_reference", "ok"} <= set(line["parity"])
+    assert ("strong" in line) == (world > 1)
+    if world > 1:
+        assert {"value", "n1_value", "efficiency_vs_n1"} <= set(line["strong"])
     if world == 1:
         assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
         assert line["roofline"]["traffic"] and line["roofline"]["dram"]["frac"] < 1.0
+        assert line["roofline"]["frac_dram"] == line["roofline"]["dram"]["frac"]
         assert abs(line["roofline"]["frac"] - 120.0 * 512 ** 3 / 1.89e-3 / 1e9 / line["roofline"]["peak"]) < 1e-9
     else:
         assert "cpu_baseline" not in line
