@@ -134,13 +134,21 @@ __global__ void k_pad_density(const Geom g, const AsmPar P, const double* __rest
 
 // Rows from the padded density and the caller's face fluxes:
 //   vx (nzl, ny, nx+1), vy (nzl, ny+1, nx), vz (nzl+1, ny, nx); src (nzl, ny, nx) or null.
-// Same face formulas as k_rows_from_density (src/solver/proj.ipp:343-383):
-//   e7 = sum_q outward(q)*v_f - src*V   (proj.ipp:366-378)
+// The order of operations is the reference's own, so that the rows are bit for bit what
+// Proj::GetFlux + GetFluxSum produce (src/solver/proj.ipp:343-383; pinned by
+// oracle/_ref/ref_assemble, see aphros_b200/systems.py:projection_rows):
+//   rho_f = 1 / ((1/rho_+ + 1/rho_-) * 0.5)        InterpolateHarmonic, approx_eb.h:351-363
+//   k_f   = (1/h) * (((V/h) / rho_f) * dt)          GradientImplicit [-1/h, 1/h] scaled by
+//                                                   -area/rho_f*dt, area = V/h (mesh.ipp:91)
+//   e0 = sum_q k_f(q) in the order q = 0..5,  e[1+q] = -k_f(q)      AppendExpr, mesh.h:575-579
+//   e7 = (((((-v_x- + v_x+) - v_y-) + v_y+) - v_z-) + v_z+) - src*V   proj.ipp:377-379
 __global__ void k_rows_from_faces(const Geom g, const AsmPar P, const double* __restrict__ rho,
                                   const double* __restrict__ vx, const double* __restrict__ vy,
                                   const double* __restrict__ vz, const double* __restrict__ src,
                                   double vol, double* a0, double* a1, double* a2, double* a3,
                                   double* a4, double* a5, double* a6, double* rhs) {
+  const double inv_h = __ddiv_rn(1.0, P.h);
+  const double area = __ddiv_rn(vol, P.h);
   for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < g.ncell;
        c += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(c % g.nx);
@@ -148,7 +156,7 @@ __global__ void k_rows_from_faces(const Geom g, const AsmPar P, const double* __
     const int k = (int)(c / g.cz);
     const int64_t kg = P.z0 + k;
     const int64_t ip = g.poff + i + (int64_t)j * g.py + (int64_t)k * g.pz;
-    const double rc = rho[ip];
+    const double inv_c = __ddiv_rn(1.0, rho[ip]);
     const int64_t off[6] = {-1, 1, -g.py, g.py, -g.pz, g.pz};
     const bool wall[6] = {!P.per[0] && i == 0,          !P.per[0] && i == P.nx_g - 1,
                           !P.per[1] && j == 0,          !P.per[1] && j == P.ny_g - 1,
@@ -157,10 +165,9 @@ __global__ void k_rows_from_faces(const Geom g, const AsmPar P, const double* __
     double diag = 0.0;
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
-      const double rn = rho[ip + off[q]];
-      const double rlo = (q & 1) ? rc : rn, rhi = (q & 1) ? rn : rc;
-      const double rf = __ddiv_rn(2.0, __dadd_rn(__ddiv_rn(1.0, rlo), __ddiv_rn(1.0, rhi)));
-      a[q] = wall[q] ? 0.0 : __ddiv_rn(__dmul_rn(P.h, P.dt), rf);
+      const double inv_n = __ddiv_rn(1.0, rho[ip + off[q]]);
+      const double rf = __ddiv_rn(1.0, __dmul_rn(__dadd_rn(inv_c, inv_n), 0.5));
+      a[q] = wall[q] ? 0.0 : __dmul_rn(inv_h, __dmul_rn(__ddiv_rn(area, rf), P.dt));
       diag = __dadd_rn(diag, a[q]);
     }
     a0[c] = diag;
@@ -172,11 +179,12 @@ __global__ void k_rows_from_faces(const Geom g, const AsmPar P, const double* __
     a6[c] = -a[5];
     const int64_t fx = i + (int64_t)j * (g.nx + 1) + (int64_t)k * (g.nx + 1) * g.ny;
     const int64_t fy = i + (int64_t)j * g.nx + (int64_t)k * g.nx * (g.ny + 1);
-    const double dx = __dsub_rn(vx[fx + 1], vx[fx]);
-    const double dy = __dsub_rn(vy[fy + g.nx], vy[fy]);
-    const double dz = __dsub_rn(vz[c + g.cz], vz[c]);
-    double e7 = __dadd_rn(__dadd_rn(dx, dy), dz);
-    if (src) e7 = __dsub_rn(e7, __dmul_rn(src[c], vol));
+    double e7 = __dadd_rn(-vx[fx], vx[fx + 1]);
+    e7 = __dsub_rn(e7, vy[fy]);
+    e7 = __dadd_rn(e7, vy[fy + g.nx]);
+    e7 = __dsub_rn(e7, vz[c]);
+    e7 = __dadd_rn(e7, vz[c + g.cz]);
+    e7 = __dsub_rn(e7, __dmul_rn(src ? src[c] : 0.0, vol));
     rhs[c] = e7;
   }
 }

@@ -19,6 +19,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = [
+    "projection_rows",
     "cell_volume",
     "tlinear_system",
     "density_poisson_system",
@@ -219,3 +220,60 @@ def periodic_constant_system(n, shape=None, dt=1.0):
     exact = _exact_tlinear(nz, ny, nx, h)
     sys[..., 7] = -_apply(sys, exact, per)
     return sys, exact
+
+
+def projection_rows(rho, vx, vy, vz, source=None, dt=1e-3, periodic=(False, False, False),
+                    h=None, volume=None):
+    """Rows of the projection step's pressure system from a cell density and face volume
+    fluxes, in the reference's own order of operations (Proj::GetFlux + GetFluxSum,
+    src/solver/proj.ipp:343-383, on a uniform mesh without embedded boundaries; every
+    non-periodic domain face a wall):
+
+        rho_f = 1 / ((1/rho_+ + 1/rho_-) * 0.5)           (approx_eb.h:351-363, ipp:834-836)
+        k_f   = (1/h) * (((V/h) / rho_f) * dt)             (approx_eb.ipp:1440-1444, proj.ipp:356;
+                                                            face area = V / h, mesh.ipp:91)
+        e0 = (((((k_x- + k_x+) + k_y-) + k_y+) + k_z-) + k_z+     (AppendExpr, mesh.h:575-579)
+        e[1+q] = -k_f(q)
+        e7 = (((((-v_x- + v_x+) - v_y-) + v_y+) - v_z-) + v_z+) - source*V   (proj.ipp:377-379)
+
+    This is the host statement of what aphcg_assemble_projection computes on the device; it is
+    pinned bit for bit to the reference's functions by tests/test_oracle.py
+    (oracle/_ref/ref_assemble and tests/golden/assemble_*.npz).
+    rho (nz,ny,nx); vx (nz,ny,nx+1), vy (nz,ny+1,nx), vz (nz+1,ny,nx).  Returns (nz,ny,nx,8)."""
+    rho = np.asarray(rho, dtype=np.float64)
+    shape = rho.shape
+    nz, ny, nx = shape
+    h = 1.0 / max(shape) if h is None else float(h)
+    vol = cell_volume(shape) if volume is None else float(volume)
+    area = vol / h
+    inv = 1.0 / rho
+    rows = np.zeros(shape + (8,), dtype=np.float64)
+    diag = np.zeros(shape, dtype=np.float64)
+    axis_of = {0: 2, 1: 1, 2: 0}
+    for d in range(3):
+        ax = axis_of[d]
+        # lower face of every cell: between the cell (plus side) and its lower neighbour
+        inv_m = np.roll(inv, 1, axis=ax)
+        rho_f = 1.0 / ((inv + inv_m) * 0.5)
+        k_lo = (1.0 / h) * ((area / rho_f) * dt)
+        if not periodic[d]:
+            idx = [slice(None)] * 3
+            idx[ax] = 0
+            k_lo[tuple(idx)] = 0.0
+        k_hi = np.roll(k_lo, -1, axis=ax)
+        rows[..., 1 + 2 * d] = -k_lo
+        rows[..., 2 + 2 * d] = -k_hi
+        diag = diag + k_lo
+        diag = diag + k_hi
+    rows[..., 0] = diag
+    e7 = -vx[:, :, :-1] + vx[:, :, 1:]
+    e7 = e7 - vy[:, :-1, :]
+    e7 = e7 + vy[:, 1:, :]
+    e7 = e7 - vz[:-1]
+    e7 = e7 + vz[1:]
+    if source is not None:
+        e7 = e7 - np.asarray(source, dtype=np.float64) * vol
+    else:
+        e7 = e7 - 0.0 * vol
+    rows[..., 7] = e7
+    return rows

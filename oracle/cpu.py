@@ -120,6 +120,51 @@ def apply(system, v, *, periodic=(True, True, True)):
     return out
 
 
+REF_ASSEMBLE = os.path.join(REF_DIR, "ref_assemble")
+
+
+def have_reference_assembler():
+    return os.path.exists(REF_ASSEMBLE)
+
+
+def assemble_reference(rho, vx, vy, vz, source=None, *, dt=1e-3, periodic=(False, False, False),
+                       block=None):
+    """Rows of the projection pressure system assembled by the reference's own functions
+    (oracle/_ref/ref_assemble: InterpolateHarmonic, GradientImplicit, AppendExpr in the
+    sequence of Proj::GetFlux/GetFluxSum, src/solver/proj.ipp:343-383) from a cell density
+    (nz,ny,nx) and face volume fluxes vx (nz,ny,nx+1), vy (nz,ny+1,nx), vz (nz+1,ny,nx).
+    Mesh extent 1 (h = 1/max(n)); non-periodic domain faces are walls.  Returns (nz,ny,nx,8)."""
+    rho = np.ascontiguousarray(rho, dtype=np.float64)
+    nz, ny, nx = rho.shape
+    b = block if block is not None else (nx, ny, nz)
+    if isinstance(b, int):
+        b = (b, b, b)
+    with tempfile.TemporaryDirectory() as tmp:
+        files = {}
+        for name, a, shp in (("rho", rho, (nz, ny, nx)), ("vx", vx, (nz, ny, nx + 1)),
+                             ("vy", vy, (nz, ny + 1, nx)), ("vz", vz, (nz + 1, ny, nx)),
+                             ("src", source, (nz, ny, nx))):
+            if a is None:
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != shp:
+                raise ValueError("%s: expected shape %s, got %s" % (name, shp, a.shape))
+            files[name] = os.path.join(tmp, name + ".f64")
+            a.tofile(files[name])
+        out = os.path.join(tmp, "rows.f64")
+        cmd = [REF_ASSEMBLE, "--nx", str(nx), "--ny", str(ny), "--nz", str(nz),
+               "--bsx", str(b[0]), "--bsy", str(b[1]), "--bsz", str(b[2]), "--dt", repr(float(dt)),
+               "--px", str(int(periodic[0])), "--py", str(int(periodic[1])),
+               "--pz", str(int(periodic[2])), "--out", out]
+        for name, path in files.items():
+            cmd += ["--" + name, path]
+        p = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True,
+                           env=dict(os.environ, OMP_NUM_THREADS="1"))
+        if p.returncode != 0:
+            raise RuntimeError("ref_assemble failed:\n" + p.stdout + p.stderr)
+        return np.fromfile(out, dtype=np.float64).reshape(nz, ny, nx, 8)
+
+
 def have_reference():
     return os.path.exists(REF_CG)
 

@@ -8,6 +8,12 @@ Each fixture stores the inputs' recipe (regenerated from seeds by
 aphros_b200.systems, checked by a checksum), the reference's iteration count,
 final residual and solution.  Small on purpose (<= 24^3), except
 
+    python tests/golden/make_golden.py assembly   (seconds; needs oracle/_ref/ref_assemble)
+
+which writes assemble_*.npz: rows of the projection pressure system assembled by the
+reference's own functions (oracle/ref/ref_assemble.cpp) from a seeded density and seeded face
+fluxes -- a SHA-256 per row component (the comparison is bit for bit) plus the first 64 rows; and
+
     python tests/golden/make_golden.py large      (about 10 minutes, 8 cores, 12 GB)
 
 which adds
@@ -109,6 +115,48 @@ def main_large():
         print(name, it, res, "%.1f s" % sec, flush=True)
 
 
+ASSEMBLY_CASES = ["assemble_walls32", "assemble_perz32_b16", "assemble_perxz_ragged"]
+
+
+def build_assembly_case(name):
+    """name -> dict(rho, vx, vy, vz, source, dt, periodic, block): inputs of the projection
+    assembly (density spanning 4 orders of magnitude, random face fluxes)"""
+    shape, per, block = {
+        "assemble_walls32": ((32, 32, 32), (False, False, False), None),
+        "assemble_perz32_b16": ((32, 32, 32), (False, False, True), 16),
+        "assemble_perxz_ragged": ((12, 10, 16), (True, False, True), None),
+    }[name]
+    nz, ny, nx = shape
+    rng = np.random.default_rng(20240700 + len(name))
+    rho = np.exp(rng.standard_normal(shape) * 2)
+    vx = rng.standard_normal((nz, ny, nx + 1))
+    vy = rng.standard_normal((nz, ny + 1, nx))
+    vz = rng.standard_normal((nz + 1, ny, nx))
+    if per[0]:
+        vx[:, :, -1] = vx[:, :, 0]
+    if per[1]:
+        vy[:, -1, :] = vy[:, 0, :]
+    if per[2]:
+        vz[-1] = vz[0]
+    src = rng.standard_normal(shape)
+    return dict(rho=rho, vx=vx, vy=vy, vz=vz, source=src, dt=1e-3, periodic=per, block=block)
+
+
+def main_assembly():
+    assert cpu.have_reference_assembler(), "build oracle/_ref first: make -C oracle/ref app"
+    for name in ASSEMBLY_CASES:
+        c = build_assembly_case(name)
+        rows = cpu.assemble_reference(c["rho"], c["vx"], c["vy"], c["vz"], c["source"], dt=c["dt"],
+                                      periodic=c["periodic"], block=c["block"])
+        np.savez_compressed(os.path.join(HERE, name + ".npz"),
+                            # "+ 0.0": a zero wall coefficient may be -0.0 or +0.0
+                            sha256=np.array([checksum(rows[..., q] + 0.0) for q in range(8)]),
+                            first_rows=rows.reshape(-1, 8)[:64],
+                            inputs_sha256=checksum(np.concatenate(
+                                [c[k].ravel() for k in ("rho", "vx", "vy", "vz", "source")])))
+        print(name, rows.shape, float(np.abs(rows[..., 0]).max()))
+
+
 CASES = ["tlinear16_b8", "tlinear24_b12_guess", "tlinear_ragged", "density24_neumann",
          "density16_1000to1_fixed", "const20_periodic_maxnorm", "tlinear16_miniter",
          "tlinear16_jacobi"]
@@ -131,5 +179,7 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "large":
         main_large()
+    elif len(sys.argv) > 1 and sys.argv[1] == "assembly":
+        main_assembly()
     else:
         main()

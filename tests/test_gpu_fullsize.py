@@ -74,8 +74,14 @@ def test_config2_256_variable_density(gpu):
 
 def test_config5_384_periodic(gpu):
     """config 5: 384^3 triply periodic constant-density projection solve, with the
-    reference test's exact solution as right-hand side (src/test/linear/main.cpp:47-52)"""
+    reference test's exact solution as right-hand side (src/test/linear/main.cpp:47-52,80-84);
+    "iterations-to-tolerance vs reference": the reference's own SolverConjugate (oracle/_ref/
+    ref_cg, 32^3 blocks, OpenMP) needs 942 iterations to 1e-7 x the initial residual on this
+    system -- tests/golden/config5_384_periodic.npz, written by `make_golden.py large`"""
+    import os
     from oracle import cpu
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                "config5_384_periodic.npz"))
     n = 384
     shape = (n, n, n)
     system, exact = systems.periodic_constant_system(n)
@@ -87,6 +93,16 @@ def test_config5_384_periodic(gpu):
     info = solver.Solve(system, None, x)
     hist = solver.History(info.iter)
     assert info.residual < conf.tol
+    # the headline quantity of config 5: iterations to tolerance within +-2 of the reference's
+    assert abs(conf.tol - float(gold["tol"])) <= 1e-12 * conf.tol
+    assert abs(info.iter - int(gold["iter"])) <= 2, (info.iter, int(gold["iter"]))
+    assert abs(info.residual - float(gold["residual"])) <= 1e-3 * float(gold["residual"])
+    # ... and the solution at the fixture's 4096 sample cells (same mean: CG never changes it)
+    xs = x.reshape(-1)[gold["sample_index"]]
+    assert np.abs(xs - gold["sample_x"]).max() <= 1e-10 * np.abs(exact).max()
+    print("config 5: %d iterations (reference %d), residual %.6e (reference %.6e), sample "
+          "max-abs diff %.2e" % (info.iter, int(gold["iter"]), info.residual,
+                                 float(gold["residual"]), np.abs(xs - gold["sample_x"]).max()))
     # constant diagonal: the Jacobi-preconditioned recurrence is the same iteration
     pre = SolverConjugateCuda(conf, {"jacobi_precond": True}, Mesh(shape=shape))
     xp = np.zeros(shape)

@@ -372,8 +372,9 @@ def test_precond_matches_its_oracle(gpu, flags):
 
 def test_device_assembly_from_density_and_fluxes(gpu):
     """aphcg_assemble_projection: rows assembled on the device from a
-    cell density and face fluxes equal the host generator's rows; periodic in z and
-    walls in x, y to exercise wrap and clamp"""
+    cell density and face fluxes are bit for bit the host statement's
+    (systems.projection_rows, itself pinned to the reference's assembler in test_oracle.py);
+    periodic in z and walls in x, y to exercise wrap and clamp"""
     from aphros_b200 import systems
     shape = (12, 10, 16)
     nz, ny, nx = shape
@@ -381,21 +382,13 @@ def test_device_assembly_from_density_and_fluxes(gpu):
     rng = np.random.default_rng(3)
     rho = np.exp(rng.standard_normal(shape))
     h, dt = 1.0 / max(shape), 1e-3
-    # host restatement (same formulas as systems.density_poisson_system)
-    a_lo = []
-    for d in range(3):
-        ax = {0: 2, 1: 1, 2: 0}[d]
-        rho_m = np.roll(rho, 1, axis=ax)
-        a_lo.append(h * dt / (2.0 / (1.0 / rho_m + 1.0 / rho)))
-    ref = systems._assemble(a_lo, per, 1.0, shape)
     vx = rng.standard_normal((nz, ny, nx + 1))
     vy = rng.standard_normal((nz, ny + 1, nx))
     vz = rng.standard_normal((nz + 1, ny, nx))
     vz[-1] = vz[0]                       # periodic in z: same face
     src = rng.standard_normal(shape)
     vol = systems.cell_volume(shape)
-    ref[..., 7] = ((vx[:, :, 1:] - vx[:, :, :-1]) + (vy[:, 1:, :] - vy[:, :-1, :])
-                   + (vz[1:] - vz[:-1])) - src * vol
+    ref = systems.projection_rows(rho, vx, vy, vz, src, dt=dt, periodic=per, h=h, volume=vol)
     rho_ext = np.concatenate([rho[-1:], rho, rho[:1]])   # z ghost planes (periodic images)
     solver = SolverConjugateCuda(Conf(), {}, Mesh(shape=shape, periodic=per))
     solver.AssembleProjection(rho_ext, vx, vy, vz, source=src, dt=dt, h=h)
