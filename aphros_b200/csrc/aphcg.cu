@@ -396,7 +396,7 @@ int WriteState(aphcg_t* h, const aphcg_conf* conf) {
   s.precond = h->precond ? 1 : 0;
   s.cell_volume = h->desc.cell_volume;
   s.hist_cap = h->hist_cap;
-  s.seq_base = (++h->runs) << 32;
+  s.seq_base = ++h->runs;
   s.xbatch = (h->use_tma && h->xbatch) ? 1 : 0;
   *h->h_st = s;
   CK(cudaMemcpyAsync(h->st, h->h_st, sizeof(CgState), cudaMemcpyHostToDevice, h->stream));
@@ -1084,18 +1084,22 @@ int aphcg_ipc_connect(aphcg_t* h, const void* blobs, int32_t count) {
   d.cm.rank = me;
   d.cm.nranks = n;
   d.cm.use_mail = h->use_mail ? 1 : 0;
-  // Who waits for the all-reduced scalars: the consumer kernels' own CTAs (two launches per
-  // iteration), unless the reduction is NCCL's or two slabs share a GPU -- a grid of
-  // spinning CTAs would then keep the other slab's producer kernel off the SMs for good.
+  // Who waits for the all-reduced scalars.  Default: one-warp k_finish_* kernels.  Opt-in
+  // (APHCG_WAIT=kernel): the consumer kernels' own CTAs, i.e. two launches per iteration --
+  // measured on 2 B200 (profiles/r02_wait_modes_2gpu.txt) it is no faster (64-plane slabs:
+  // 0.3995 vs 0.3969 ms/iteration; 512^3 per GPU: 2.574 vs 2.550), because every CTA then pays
+  // a system-scope fence before it may read the neighbours' planes; the hand-off cost is the
+  // cross-GPU latency itself, not the extra launches.  Never when two slabs share a GPU: a
+  // grid of spinning CTAs would keep the other slab's producer kernel off the SMs for good.
   bool shared_gpu = false;
   for (int q = 0; q < n; ++q)
     for (int w = q + 1; w < n; ++w) shared_gpu |= (b[q].pci == b[w].pci);
-  h->wait_in_kernel = h->use_mail && !shared_gpu;
-  if (const char* ew = getenv("APHCG_WAIT")) {
-    if (!strcmp(ew, "finish")) h->wait_in_kernel = false;
-    if (!strcmp(ew, "kernel") && h->use_mail && !shared_gpu) h->wait_in_kernel = true;
-  }
+  h->wait_in_kernel = false;
+  if (const char* ew = getenv("APHCG_WAIT"))
+    h->wait_in_kernel = !strcmp(ew, "kernel") && h->use_mail && !shared_gpu;
   d.cm.wait_in_kernel = h->wait_in_kernel ? 1 : 0;
+  d.cm.reader_fence = 1;
+  if (const char* ef = getenv("APHCG_WAIT_FENCE")) d.cm.reader_fence = atoi(ef) != 0;  // measurements only
   {
     const char* et = getenv("APHCG_MAIL_TIMEOUT_MS");
     const double ms = et ? atof(et) : 20000.0;

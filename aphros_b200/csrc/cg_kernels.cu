@@ -319,7 +319,7 @@ __global__ void k_finish_dir(const DevPtrs d) {
   CgState* st = d.st;
   if (st->done) return;
   double sum = st->loc_sum, mx = 0.0, sum2 = 0.0;
-  if (d.cm.use_mail && !mail_wait(d.cm, st->seq_base, st->iter, 0, &sum, &mx, &sum2)) {
+  if (d.cm.use_mail && !mail_wait(d.cm, st->seq_base, st->iter, 0, nullptr, &sum, &mx, &sum2)) {
     if (threadIdx.x == 0) st->error = st->done = 1;
     return;
   }
@@ -332,7 +332,7 @@ __global__ void k_finish_upd(const DevPtrs d) {
   // committed state when it looks; nothing to do unless an update stage is pending
   if (d.cm.wait_in_kernel && !st->pend_upd) return;
   double sum = st->loc_sum, mx = st->loc_max, sum2 = st->precond ? st->loc_sum2 : st->loc_sum;
-  if (d.cm.use_mail && !mail_wait(d.cm, st->seq_base, st->iter, 1, &sum, &mx, &sum2)) {
+  if (d.cm.use_mail && !mail_wait(d.cm, st->seq_base, st->iter, 1, nullptr, &sum, &mx, &sum2)) {
     if (threadIdx.x == 0) st->error = st->done = 1;
     return;
   }
@@ -558,7 +558,7 @@ __global__ void k_finish_jacobi(const DevPtrs d) {
   CgState* st = d.st;
   if (st->done) return;
   double sum = 0.0, mx = st->loc_max, sum2 = 0.0;
-  if (d.cm.use_mail && !mail_wait(d.cm, st->seq_base, st->iter, 0, &sum, &mx, &sum2)) {
+  if (d.cm.use_mail && !mail_wait(d.cm, st->seq_base, st->iter, 0, nullptr, &sum, &mx, &sum2)) {
     if (threadIdx.x == 0) st->error = st->done = 1;
     return;
   }

@@ -111,43 +111,103 @@ __device__ __forceinline__ double reduce_slots(const double* slots, unsigned n, 
 
 // ---- peer-memory all-reduce (see cg_types.h) -------------------------------------
 // phase 0: p.Ap (after the direction kernel), phase 1: r.r / max|r| (after the update)
-__device__ __forceinline__ unsigned long long mail_seq(unsigned long long seq_base, int iter,
-                                                       int phase) {
-  return seq_base + 2ull * (unsigned long long)iter + (unsigned long long)phase + 1ull;
+__device__ __forceinline__ unsigned mail_flag(unsigned long long run, int iter, int phase) {
+  // never 0 (fresh memory); differs between the two uses of a slot that can be confused: the
+  // same slot two iterations earlier, and the last iterations of the previous run
+  return 0x80000000u | (((unsigned)run & 0x7ffu) << 20) |
+         ((2u * (unsigned)iter + (unsigned)phase + 1u) & 0xfffffu);
 }
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void mail_store(MailWord* p, double v, unsigned flag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p),
+               "r"((unsigned)b), "r"(flag), "r"((unsigned)(b >> 32)), "r"(flag)
+               : "memory");
+}
+__device__ __forceinline__ MailWord mail_load(const MailWord* p) {
+  MailWord w;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(w.lo), "=r"(w.f0), "=r"(w.hi), "=r"(w.f1)
+               : "l"(p)
+               : "memory");
+  return w;
+}
+__device__ __forceinline__ double mail_value(const MailWord& w) {
+  return __longlong_as_double((long long)(((unsigned long long)w.hi << 32) | w.lo));
+}
+__device__ __forceinline__ MailSlot* mail_slot(MailSlot* box, int phase, int parity, int src) {
+  return box + ((phase * 2 + parity) * kMaxRanks + src);
+}
 // Called by every thread of the CTA that finished the local reduction of iteration `iter`.
-__device__ __forceinline__ void mail_push(const Comm& cm, unsigned long long seq_base, int iter,
+__device__ __forceinline__ void mail_push(const Comm& cm, unsigned long long run, int iter,
                                           int phase, double sum, double mx, double sum2 = 0.0) {
   const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
   if (tid < cm.nranks) {
-    MailSlot* s = cm.box[tid] + ((phase * 2 + (iter & 1)) * kMaxRanks + cm.rank);
-    *reinterpret_cast<volatile double*>(&s->sum) = sum;
-    *reinterpret_cast<volatile double*>(&s->mx) = mx;
-    *reinterpret_cast<volatile double*>(&s->sum2) = sum2;
-    __threadfence_system();  // values (and this kernel's halo stores) before the flag
-    *reinterpret_cast<volatile unsigned long long*>(&s->seq) = mail_seq(seq_base, iter, phase);
+    MailSlot* s = mail_slot(cm.box[tid], phase, iter & 1, cm.rank);
+    const unsigned flag = mail_flag(run, iter, phase);
+    __threadfence_system();  // this kernel's halo stores (ordered before the ticket) first
+    mail_store(&s->w[0], sum, flag);
+    mail_store(&s->w[1], mx, flag);
+    mail_store(&s->w[2], sum2, flag);
   }
 }
-// Called by one full warp.  Waits for every rank's contribution of (iter, phase) in the LOCAL
-// mailbox and adds them in rank order.  Returns false on timeout (a peer died or never ran:
-// the wall-clock limit cm.timeout_ns keeps the GPU from hanging).
-__device__ __forceinline__ bool mail_wait(const Comm& cm, unsigned long long seq_base, int iter,
-                                          int phase, double* sum, double* mx, double* sum2) {
+// What a lane of the waiting warp has read of "its" source rank's slots.  Peeking at both
+// parities costs nothing and needs no loop state, so a CTA can issue these loads together
+// with its loads of the state instead of after them (one memory round trip less at every
+// CTA start; in the steady state the data is already there).
+struct MailPeek {
+  MailWord w[2][3];
+};
+__device__ __forceinline__ MailPeek mail_peek(const Comm& cm, int phase) {
+  MailPeek pk;
   const int lane = threadIdx.x & 31;
-  const unsigned long long want = mail_seq(seq_base, iter, phase);
+  if (lane < cm.nranks) {
+#pragma unroll
+    for (int par = 0; par < 2; ++par) {
+      const MailSlot* s = mail_slot(cm.box[cm.rank], phase, par, lane);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) pk.w[par][j] = mail_load(&s->w[j]);
+    }
+  }
+  return pk;
+}
+__device__ __forceinline__ bool mail_complete(const MailWord* w, unsigned flag) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) ok = ok && w[j].f0 == flag && w[j].f1 == flag;
+  return ok;
+}
+// Called by one full warp.  Waits for every rank's contribution of (iter, phase) in the LOCAL
+// mailbox (first looking at what mail_peek already fetched) and adds them in rank order.
+// Returns false on timeout (a peer died or never ran: the wall-clock limit cm.timeout_ns keeps
+// the GPU from hanging).
+__device__ __forceinline__ bool mail_wait(const Comm& cm, unsigned long long run, int iter,
+                                          int phase, const MailPeek* peek, double* sum, double* mx,
+                                          double* sum2) {
+  const int lane = threadIdx.x & 31;
+  const unsigned flag = mail_flag(run, iter, phase);
   double vs = 0.0, vm = 0.0, v2 = 0.0;
   bool ok = true;
   if (lane < cm.nranks) {
-    MailSlot* s = cm.box[cm.rank] + ((phase * 2 + (iter & 1)) * kMaxRanks + lane);
+    MailWord w[3];
+    bool have = false;
+    if (peek) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) w[j] = (iter & 1) ? peek->w[1][j] : peek->w[0][j];
+      have = mail_complete(w, flag);
+    }
+    const MailSlot* s = mail_slot(cm.box[cm.rank], phase, iter & 1, lane);
     unsigned long long t0 = 0;
     unsigned spins = 0;
-    while (*reinterpret_cast<volatile unsigned long long*>(&s->seq) != want) {
-      if ((++spins & 1023u) == 0) {
+    while (!have) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) w[j] = mail_load(&s->w[j]);
+      have = mail_complete(w, flag);
+      if (!have && (++spins & 1023u) == 0) {
         const unsigned long long now = global_ns();
         if (t0 == 0) t0 = now;
         if (now - t0 > cm.timeout_ns) {
@@ -156,10 +216,9 @@ __device__ __forceinline__ bool mail_wait(const Comm& cm, unsigned long long seq
         }
       }
     }
-    __threadfence_system();
-    vs = *reinterpret_cast<volatile double*>(&s->sum);
-    vm = *reinterpret_cast<volatile double*>(&s->mx);
-    v2 = *reinterpret_cast<volatile double*>(&s->sum2);
+    vs = mail_value(w[0]);
+    vm = mail_value(w[1]);
+    v2 = mail_value(w[2]);
   }
   ok = __all_sync(0xffffffffu, ok);
   double ts = 0.0, tm = 0.0, t2 = 0.0;
@@ -247,6 +306,8 @@ __device__ __forceinline__ void dir_view(const DevPtrs& d, DirView* sv) {
   const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
   if (tid < 32) {
     const CgState* st = d.st;
+    MailPeek peek;
+    if (d.cm.wait_in_kernel) peek = mail_peek(d.cm, 1);  // in flight together with the state
     DirView v;
     v.pend = st->pend_upd;
     v.error = 0;
@@ -258,7 +319,9 @@ __device__ __forceinline__ void dir_view(const DevPtrs& d, DirView* sv) {
       v.alpha_prev2 = st->alpha_prev2;
     } else {
       double sum, mx, sum2;
-      const bool ok = mail_wait(d.cm, st->seq_base, st->iter, 1, &sum, &mx, &sum2);
+      const bool ok = mail_wait(d.cm, st->seq_base, st->iter, 1, &peek, &sum, &mx, &sum2);
+      // the neighbours' boundary planes of r were stored before their flags
+      if (d.cm.reader_fence) __threadfence_system();
       v.next = cg_step(st, sum, mx, st->precond ? sum2 : sum);
       if (!ok) {
         v.next.done = 1;
@@ -310,6 +373,8 @@ __device__ __forceinline__ void upd_view(const DevPtrs& d, UpdView* sv) {
   const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
   if (tid < 32) {
     const CgState* st = d.st;
+    MailPeek peek;
+    if (d.cm.wait_in_kernel) peek = mail_peek(d.cm, 0);
     UpdView v;
     v.pend = st->pend_dir;
     v.iter = st->iter;
@@ -318,7 +383,7 @@ __device__ __forceinline__ void upd_view(const DevPtrs& d, UpdView* sv) {
       v.pAp = st->pAp;
     } else {
       double sum, mx, sum2;
-      if (!mail_wait(d.cm, st->seq_base, st->iter, 0, &sum, &mx, &sum2)) v.error = 1;
+      if (!mail_wait(d.cm, st->seq_base, st->iter, 0, &peek, &sum, &mx, &sum2)) v.error = 1;
       v.pAp = sum;
     }
     v.alpha = st->rr / (v.pAp + 1e-100);  // linear.ipp:84

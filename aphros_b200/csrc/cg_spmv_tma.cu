@@ -501,10 +501,14 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
   if (const char* env = getenv("APHCG_ZC")) {
     zc = atoi(env);
   } else {
+    // 64 planes per CTA only when that makes the whole grid ONE wave (measured, round 2:
+    // 64x512x512 0.261 vs 0.271 ms, 256^3 0.270 vs 0.280; but 128x512x512 -- two waves
+    // either way -- 0.526 vs 0.507).
     int64_t best = -1;
-    for (int z = 32; z >= 2; z /= 2) {
+    const int64_t slots = 2 * kNumSMs;  // resident CTAs of this kernel (2 per SM)
+    for (int z = 64; z >= 2; z /= 2) {
       const int64_t n = (int64_t)tiles * ((g.nzl + z - 1) / z);
-      const int64_t slots = 2 * kNumSMs;  // resident CTAs of this kernel (2 per SM)
+      if (z == 64 && n > slots) continue;
       const int64_t cost = ((n + slots - 1) / slots) * (z + 4);
       if (best < 0 || cost < best) {
         best = cost;

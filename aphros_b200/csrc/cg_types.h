@@ -39,10 +39,17 @@ struct Geom {
 // of the current step have arrived in its LOCAL array and adds the values in rank
 // order, so every rank forms bitwise the same sum without a collective call.
 constexpr int kMaxRanks = 16;
-struct MailSlot {
-  double sum, mx;
-  unsigned long long seq;
-  double sum2;
+// One double travels as 16 bytes: its two halves, each followed by a copy of a 32-bit flag
+// that identifies (run, iteration, phase) -- the "low latency" idea of NCCL's LL protocol.  The
+// writer stores the 16 bytes with one vector store; the reader needs no fence between flag and
+// data because each 8-byte half {data, flag} is written and read as a unit: a half whose flag
+// is the expected one carries the data of that very store.
+struct alignas(16) MailWord {
+  unsigned lo, f0, hi, f1;
+};
+struct alignas(64) MailSlot {
+  MailWord w[3];  // sum, max, second sum
+  unsigned pad[4];
 };
 constexpr int kMailSlots = 2 * 2 * kMaxRanks;  // [phase][parity][source rank]
 struct Comm {
@@ -55,6 +62,9 @@ struct Comm {
   //    reduction, or slabs that share one GPU: a grid of spinning CTAs would keep the peer
   //    slab's producer kernel off the SMs)
   int wait_in_kernel;
+  // 1 (always, except for measurements: APHCG_WAIT_FENCE=0): system-scope fence between the
+  // arrival of the neighbours' flags and the first read of this slab's ghost planes of r
+  int reader_fence;
   unsigned long long timeout_ns;  // a wait that sees nothing for this long flags APHCG_ERR_COMM
 };
 
@@ -94,7 +104,7 @@ struct CgState {
                  // -- the same FMAs in the same order as one per iteration, so x is bitwise
                  // unchanged, but x is read and written every other iteration (p_{k-2} is
                  // still in the buffer p_k is about to overwrite): 12 instead of 16 B/cell
-  unsigned long long seq_base;  // distinguishes the mailbox traffic of successive runs
+  unsigned long long seq_base;  // run number: distinguishes the mailbox traffic of successive runs
   // Comm::wait_in_kernel: this rank's partial result of the direction / update stage has been
   // pushed, but the all-reduced value is not folded into the state above yet -- the consumer
   // kernel's CTAs fold it for themselves and its last CTA commits it (cg_kernels.cuh)
