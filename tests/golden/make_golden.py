@@ -17,9 +17,12 @@ fluxes -- a SHA-256 per row component (the comparison is bit for bit) plus the f
     python tests/golden/make_golden.py large      (about 10 minutes, 8 cores, 12 GB)
 
 which adds
-  * bench_parity_64: a 64^3 variable-density system (10:1, walls) solved to 1e-10 x the
-    initial residual -- the system bench.py cuts into z-slabs at N > 1 for its untimed parity
-    check (iteration count, residual and the whole solution: 2 MB);
+  * bench_parity_tlinear64 and bench_parity_64: the two 64^3 systems bench.py cuts into
+    z-slabs for its untimed parity check -- the reference unit test's own system (periodic,
+    10:1 resistivity, to 1e-12 x the initial residual) and a variable-density system with
+    walls (10:1, to 1e-10): iteration count, residual and the whole solution (2 MB each); for
+    the second one also the reference's iteration counts for block sizes 8/16/32/64, because
+    there its own count moves with the summation order (1726..1732);
   * config5_384_periodic: BASELINE.json config 5 ("384^3 periodic projection solve,
     iterations-to-tolerance vs reference"): the reference's iteration count and residual at
     tol = 1e-7 x initial residual, plus the solution at 4096 sample cells (not the 453 MB field).
@@ -74,6 +77,11 @@ def build_case(name):
 
 
 def build_large(name):
+    if name == "bench_parity_tlinear64":
+        shape = (64, 64, 64)
+        s, _ = systems.tlinear_system(64)
+        tol = 1e-12 * float(np.sqrt((s[..., 7] ** 2).sum() / systems.cell_volume(shape)))
+        return s, None, (True, True, True), dict(tol=tol, maxiter=5000, block=16)
     if name == "bench_parity_64":
         shape = (64, 64, 64)
         s, _ = systems.density_poisson_system(None, nspheres=6, seed=4, rho_in=0.1, shape=shape)
@@ -96,7 +104,8 @@ def main_large():
     assert cpu.have_reference(), "build oracle/_ref first: make -C oracle/ref"
     threads = os.cpu_count() or 1
     workdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
-    for name in ["bench_parity_64", "config5_384_periodic"]:
+    names = sys.argv[2:] or ["bench_parity_tlinear64", "bench_parity_64", "config5_384_periodic"]
+    for name in names:
         s, x0, per, kw = build_large(name)
         x, it, res, sec = cpu.solve_reference(s, x0, periodic=per, threads=threads, workdir=workdir,
                                               **kw)
@@ -105,6 +114,15 @@ def main_large():
         if x.size <= 64 ** 3:
             out["x"] = x
             out["system_sha256"] = checksum(s)
+            # the reference's own iteration count for other block sizes (summation orders)
+            blocks = [8, 16, 32, 64]
+            out["blocks"] = np.array(blocks)
+            out["iter_by_block"] = np.array([
+                it if b == kw["block"] else cpu.solve_reference(
+                    s, x0, periodic=per, threads=threads, workdir=workdir, **dict(kw, block=b))[1]
+                for b in blocks])
+            print(name, "iterations by block size", dict(zip(blocks, out["iter_by_block"].tolist())),
+                  flush=True)
         else:
             idx = sample_index(x.shape)
             out["sample_index"] = idx
