@@ -118,6 +118,8 @@ struct aphcg {
   bool allow_sym = true;
   int* d_flag = nullptr;
   TmaPlan* tma = nullptr;
+  bool persist = false;   // the loop runs as one persistent cooperative kernel (small meshes)
+  PersistPlan pplan{};
   // comm
   ncclComm_t comm = nullptr;
   GroupSync* gs = nullptr;             // in-process slab group (aphcg_group_*): replaces NCCL
@@ -397,7 +399,7 @@ int WriteState(aphcg_t* h, const aphcg_conf* conf) {
   s.cell_volume = h->desc.cell_volume;
   s.hist_cap = h->hist_cap;
   s.seq_base = ++h->runs;
-  s.xbatch = (h->use_tma && h->xbatch) ? 1 : 0;
+  s.xbatch = (h->use_tma && h->xbatch && !h->persist) ? 1 : 0;
   *h->h_st = s;
   CK(cudaMemcpyAsync(h->st, h->h_st, sizeof(CgState), cudaMemcpyHostToDevice, h->stream));
   return 0;
@@ -421,7 +423,27 @@ int EnsureHistory(aphcg_t* h, int maxiter) {
 }
 
 // Replays iterations until the device-side exit rule fires.
+// The persistent kernel stops by itself; the host only bounds a launch (so that a
+// tolerance-driven solve is looked at now and then) and repeats until the exit flag is set.
+int RunLoopPersistent(aphcg_t* h, const aphcg_conf* conf) {
+  const long limit = std::max<long>((long)conf->maxiter + 1, (long)conf->miniter);
+  long enq = 0;
+  for (;;) {
+    const int n = (int)std::min<long>(limit - enq > 0 ? limit - enq : 1, 4096);
+    CK(launch_cg_persistent(h->g, h->d, h->vx, h->pplan, n, h->stream));
+    h->launches++;
+    enq += n;
+    CK(cudaMemcpyAsync(h->h_st, h->st, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_st->done) break;
+    if (enq > limit + 4096)
+      return Fail(APHCG_ERR_STATE, "loop did not terminate (iter=%d)", h->h_st->iter);
+  }
+  return 0;
+}
+
 int RunLoop(aphcg_t* h, bool jacobi, const aphcg_conf* conf) {
+  if (h->persist && !jacobi) return RunLoopPersistent(h, conf);
   cudaGraphExec_t* gx = jacobi ? &h->gexec_jacobi : (h->sym ? &h->gexec_sym : &h->gexec);
   if (h->use_graph && !*gx) {
     if (int rc = BuildGraph(h, jacobi, gx)) return rc;
@@ -578,6 +600,17 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
     } else if (env && !strcmp(env, "tma")) {
       return cleanup(Fail(APHCG_ERR_CUDA, "TMA kernel requested but unavailable: %s", err));
     }
+  }
+  // Small single-GPU meshes: the whole loop as one persistent cooperative kernel (DESIGN.md
+  // section 3).  Limit: the fields (13 arrays) should stay in the 126 MB L2.
+  {
+    int64_t max_cells = 1200000;
+    if (const char* ep = getenv("APHCG_PERSISTENT")) max_cells = atoll(ep) == 1 ? max_cells : atoll(ep);
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ds.device);
+    h->persist = h->single && !h->precond && coop && !(ds.flags & APHCG_NO_PERSISTENT) &&
+                 g.ncell <= max_cells && persistent_plan(g, h->vx, &h->pplan);
+    if (h->persist) h->nslots = std::max(h->nslots, h->pplan.grid);
   }
   CKC(cudaMalloc(&h->partials, sizeof(double) * h->nslots));
   CKC(cudaMalloc(&h->partials2, sizeof(double) * h->nslots));
@@ -1191,6 +1224,13 @@ int aphcg_describe(aphcg_t* h, char* buf, int32_t buflen) {
   if (!h || !buf || buflen < 1) return Fail(APHCG_ERR_ARG, "bad argument");
   char t[160] = "";
   if (h->use_tma) tma_plan_describe(h->tma, t, sizeof(t));
+  if (h->persist) {
+    snprintf(buf, buflen,
+             "loop=persistent-cooperative ctas=%u planes_per_tile=%d update_rows=%d (two grid "
+             "barriers per iteration, plain-load stencil) precond=none allreduce=none",
+             h->pplan.grid, h->pplan.zc, h->pplan.ur);
+    return 0;
+  }
   snprintf(buf, buflen, "spmv=%s%s %s precond=%s graph=%d allreduce=%s", h->use_tma ? "tma" : "plain",
            h->use_tma ? (h->sym ? "-sym4" : "-gen7") : "", t, h->precond ? "jacobi" : "none",
            h->use_graph ? 1 : 0,
@@ -1203,7 +1243,7 @@ int aphcg_describe(aphcg_t* h, char* buf, int32_t buflen) {
 
 void* aphcg_stream(aphcg_t* h) { return h ? (void*)h->stream : nullptr; }
 int64_t aphcg_launch_count(aphcg_t* h) { return h ? h->launches : 0; }
-int aphcg_launches_per_iter(aphcg_t* h) { return h ? LaunchesPerIter(h) : 0; }
+int aphcg_launches_per_iter(aphcg_t* h) { return h ? (h->persist ? 0 : LaunchesPerIter(h)) : 0; }
 
 }  // extern "C"
 

@@ -16,10 +16,14 @@
 // r and p_old (bitwise the same numbers the owner computes), and ghost layers of
 // r are written by k_update itself -- into this GPU's own ghost cells for
 // periodic wrap, or straight into the neighbour GPU's ghost plane over NVLink.
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "cg_kernels.cuh"
 #include "cg_launch.h"
+
+namespace cg = cooperative_groups;
 
 namespace acg {
 
@@ -33,15 +37,21 @@ struct Tile {
   bool active;
 };
 
+// tile (bx, by, bz) of the tiled kernels' grid; tx, ty: this thread inside the kBX x kBY block
 template <int VX>
-__device__ __forceinline__ Tile my_tile(const Geom& g) {
+__device__ __forceinline__ Tile tile_at(const Geom& g, int bx, int by, int bz, int tx, int ty,
+                                        int zc) {
   Tile t;
-  t.i = (blockIdx.x * kBX + threadIdx.x) * VX;
-  t.j = blockIdx.y * kBY + threadIdx.y;
-  t.k0 = blockIdx.z * g.zc;
-  t.k1 = min(t.k0 + g.zc, g.nzl);
+  t.i = (bx * kBX + tx) * VX;
+  t.j = by * kBY + ty;
+  t.k0 = bz * zc;
+  t.k1 = min(t.k0 + zc, g.nzl);
   t.active = (t.i < g.nx) && (t.j < g.ny);
   return t;
+}
+template <int VX>
+__device__ __forceinline__ Tile my_tile(const Geom& g) {
+  return tile_at<VX>(g, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, threadIdx.y, g.zc);
 }
 
 __device__ __forceinline__ unsigned num_blocks() { return gridDim.x * gridDim.y * gridDim.z; }
@@ -73,25 +83,17 @@ __device__ __forceinline__ void store_images(const Geom& g, double* f, int64_t i
 // ------------------------------------------------------------------------------
 // k_dir_spmv (plain-load variant): neighbours of p come through L1/L2.
 // ------------------------------------------------------------------------------
-template <int VX, bool kSingle>
-__global__ void __launch_bounds__(kBX* kBY)
-    k_dir_spmv_plain(const Geom g, const DevPtrs d) {
-  __shared__ double sm[32];
-  __shared__ int sm_flag;
-  __shared__ DirView view;
-  CgState* st = d.st;
-  if (st->done) return;
-  dir_view(d, &view);
-  const double beta = view.beta;
-  const double alpha_prev = view.alpha_prev;
-  const int par = view.iter & 1;
+// One tile of the direction + SpMV stage with plain loads; returns this thread's part of
+// sum p.Ap.  Shared by the stand-alone kernel and the persistent small-mesh kernel.
+template <int VX>
+__device__ __forceinline__ double dir_spmv_tile(const Geom& g, const DevPtrs& d, const Tile& t,
+                                                const double beta, const double alpha_prev,
+                                                const int par) {
   const double* __restrict__ po = d.p[par];
   double* __restrict__ pn = d.p[par ^ 1];
   const double* __restrict__ r = d.r;
-
-  const Tile t = my_tile<VX>(g);
   double acc = 0.0;
-  if (t.active && !view.done) {
+  if (t.active) {
     for (int k = t.k0; k < t.k1; ++k) {
       const int64_t idc = t.i + t.j * g.cy + k * g.cz;
       const int64_t idp = g.poff + t.i + t.j * g.py + k * g.pz;
@@ -147,6 +149,21 @@ __global__ void __launch_bounds__(kBX* kBY)
       if (k == g.nzl - 1) stv<VX>(pn + idp + g.pz, pzp);
     }
   }
+  return acc;
+}
+
+template <int VX, bool kSingle>
+__global__ void __launch_bounds__(kBX* kBY)
+    k_dir_spmv_plain(const Geom g, const DevPtrs d) {
+  __shared__ double sm[32];
+  __shared__ int sm_flag;
+  __shared__ DirView view;
+  CgState* st = d.st;
+  if (st->done) return;
+  dir_view(d, &view);
+  double acc = 0.0;
+  if (!view.done)
+    acc = dir_spmv_tile<VX>(g, d, my_tile<VX>(g), view.beta, view.alpha_prev, view.iter & 1);
   const double bsum = block_reduce<false>(acc, sm);
   const int tid = threadIdx.x + blockDim.x * threadIdx.y;
   if (tid == 0) d.partials[block_id()] = bsum;
@@ -169,26 +186,23 @@ constexpr int kUT = 256;  // threads
 // kPre (opt-in Jacobi preconditioner, z = r/diag): the true residual lives in the
 // compact array d.rc, the padded field d.r carries z (it is what the direction
 // kernel combines with p_old), and the sums are r.z (-> alpha, beta) and r.r (-> norm).
-template <int VX, bool kSingle, int UR, bool kPre>
-__global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
-  __shared__ double sm[32];
-  __shared__ int sm_flag;
-  __shared__ UpdView view;
-  CgState* st = d.st;
-  if (st->done) return;
-  upd_view(d, &view);
-  const double alpha = view.alpha;
+// The update stage over the work items first, first + stride, ... (an item = UR rows of one
+// x-chunk of one plane): r -= alpha*Ap with the partial sums of r.r (or r.z, kPre) and max|r|.
+// Shared by the stand-alone persistent-grid kernel and the persistent small-mesh kernel.
+template <int VX, int UR, bool kPre>
+__device__ __forceinline__ void update_items(const Geom& g, const DevPtrs& d, const double alpha,
+                                             const int64_t first, const int64_t stride,
+                                             const int64_t nwork, double& acc, double& amax,
+                                             double& acc2) {
   double* __restrict__ r = d.r;
-  double acc2 = 0.0;
   // g.utx threads span one row segment; on narrow meshes (nx/VX < kUT) the remaining
   // kUT/g.utx thread rows of the CTA take further row groups, so no thread idles
   const int utx = g.utx, uty = kUT / utx;
-  const int tx = threadIdx.x % utx, ty = threadIdx.x / utx;
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  const int tx = tid % utx, ty = tid / utx;
   const int xchunks = (g.nx + utx * VX - 1) / (utx * VX);
   const int jgroups = (g.ny + UR * uty - 1) / (UR * uty);
-  const int64_t nwork = view.error ? 0 : (int64_t)xchunks * jgroups * g.nzl;
-  double acc = 0.0, amax = 0.0;
-  for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+  for (int64_t w = first; w < nwork; w += stride) {
     const int xc = (int)(w % xchunks);
     const int64_t t = w / xchunks;
     const int j0 = ((int)(t % jgroups) * uty + ty) * UR;
@@ -239,6 +253,24 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
       }
     }
   }
+}
+__host__ __device__ inline int64_t update_nwork(const Geom& g, int vx, int ur) {
+  const int uty = kUT / g.utx;
+  const int xchunks = (g.nx + g.utx * vx - 1) / (g.utx * vx);
+  return (int64_t)xchunks * ((g.ny + ur * uty - 1) / (ur * uty)) * g.nzl;
+}
+
+template <int VX, bool kSingle, int UR, bool kPre>
+__global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
+  __shared__ double sm[32];
+  __shared__ int sm_flag;
+  __shared__ UpdView view;
+  CgState* st = d.st;
+  if (st->done) return;
+  upd_view(d, &view);
+  double acc = 0.0, amax = 0.0, acc2 = 0.0;
+  update_items<VX, UR, kPre>(g, d, view.alpha, blockIdx.x, gridDim.x,
+                             view.error ? 0 : update_nwork(g, VX, UR), acc, amax, acc2);
   if (d.r_lo_dst != nullptr || d.r_hi_dst != nullptr) __threadfence_system();
   const double bsum = block_reduce<false>(acc, sm);
   const double bmax = block_reduce<true>(amax, sm);
@@ -271,6 +303,85 @@ __global__ void __launch_bounds__(kUT) k_update(const Geom g, const DevPtrs d) {
   }
 }
 
+// ------------------------------------------------------------------------------
+// k_cg_persistent: the whole loop in ONE cooperative kernel, for meshes whose fields stay in
+// the 126 MB L2 (config 1: 64^3).  There two launches per iteration plus their ramp-up cost
+// more than the work (64^3: 29 us per iteration for ~4 us of memory traffic).  Same tiles,
+// same arithmetic as k_dir_spmv_plain + k_update; the two scalar reductions per iteration
+// become grid-wide barriers after which EVERY CTA adds the per-CTA slots in the same fixed
+// order (bitwise the same sum everywhere, no broadcast needed), and every CTA carries the loop
+// scalars in registers.  Runs until the exit rule fires or `max_iters` iterations are done.
+// ------------------------------------------------------------------------------
+template <int VX, int UR>
+__global__ void __launch_bounds__(kBX* kBY, 2)
+    k_cg_persistent(const Geom g, const DevPtrs d, const dim3 tgrid, const int zc,
+                    const int max_iters) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sm[32];
+  CgState* st = d.st;
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  const unsigned G = gridDim.x;
+  const unsigned ntiles = tgrid.x * tgrid.y * tgrid.z;
+  const int64_t nwork = update_nwork(g, VX, UR);
+  // loop scalars, identical in every thread of the grid
+  double rr = st->rr, rr_prev = st->rr_prev, alpha_prev = st->alpha_prev, pAp = st->pAp;
+  double alpha_prev2 = st->alpha_prev2, rnorm2 = st->rnorm2, max_r = st->max_r;
+  double residual = st->residual;
+  int iter = st->iter, done = st->done;
+  const double tol = st->tol, vol = st->cell_volume;
+  const int miniter = st->miniter, maxiter = st->maxiter, maxnorm = st->maxnorm;
+  const int hist_cap = st->hist_cap;
+  for (int it = 0; it < max_iters && !done; ++it) {
+    // ---- stages "iter3" (of the previous iteration) + "iter" -----------------------------
+    const double beta = iter == 0 ? 0.0 : rr / (rr_prev + 1e-100);  // linear.ipp:98
+    double acc = 0.0;
+    for (unsigned vb = blockIdx.x; vb < ntiles; vb += G) {
+      const int bx = vb % tgrid.x, by = (vb / tgrid.x) % tgrid.y, bz = vb / (tgrid.x * tgrid.y);
+      acc += dir_spmv_tile<VX>(g, d, tile_at<VX>(g, bx, by, bz, threadIdx.x, threadIdx.y, zc), beta,
+                               alpha_prev, iter & 1);
+    }
+    const double bsum = block_reduce<false>(acc, sm);
+    if (tid == 0) d.partials[blockIdx.x] = bsum;
+    grid.sync();
+    pAp = reduce_slots<false>(d.partials, G, sm);
+    const double alpha = rr / (pAp + 1e-100);  // linear.ipp:84
+    // ---- stages "iter2" + "check" ------------------------------------------------------------
+    double a1 = 0.0, amax = 0.0, a2 = 0.0;
+    update_items<VX, UR, false>(g, d, alpha, blockIdx.x, G, nwork, a1, amax, a2);
+    const double bs = block_reduce<false>(a1, sm);
+    const double bm = block_reduce<true>(amax, sm);
+    if (tid == 0) {
+      d.partials2[blockIdx.x] = bm;
+      d.partials3[blockIdx.x] = bs;
+    }
+    grid.sync();
+    const double tot = reduce_slots<false>(d.partials3, G, sm);
+    const double mx = reduce_slots<true>(d.partials2, G, sm);
+    alpha_prev2 = alpha_prev;
+    alpha_prev = alpha;
+    rr_prev = rr;
+    rr = tot;
+    rnorm2 = tot;
+    max_r = mx;
+    residual = maxnorm ? mx / vol : sqrt(tot / vol);  // linear.ipp:103-107
+    ++iter;
+    if (blockIdx.x == 0 && tid == 0 && iter - 1 < hist_cap) d.history[iter - 1] = residual;
+    done = (iter >= miniter && (iter > maxiter || residual < tol)) ? 1 : 0;  // :110-113
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    st->rr = rr;
+    st->rr_prev = rr_prev;
+    st->pAp = pAp;
+    st->alpha_prev = alpha_prev;
+    st->alpha_prev2 = alpha_prev2;
+    st->rnorm2 = rnorm2;
+    st->max_r = max_r;
+    st->residual = residual;
+    st->iter = iter;
+    st->done = done;
+  }
+}
+
 static int update_ur() {
   static int ur = [] {
     const char* e = getenv("APHCG_UPD_UR");
@@ -289,10 +400,7 @@ static int update_ctas_per_sm() {
 }
 
 static dim3 update_grid(const Geom& g, int vx) {
-  const int ur = update_ur();
-  const int uty = kUT / g.utx;
-  const int xchunks = (g.nx + g.utx * vx - 1) / (g.utx * vx);
-  const int64_t nwork = (int64_t)xchunks * ((g.ny + ur * uty - 1) / (ur * uty)) * g.nzl;
+  const int64_t nwork = update_nwork(g, vx, update_ur());
   const int64_t cap = kNumSMs * (int64_t)update_ctas_per_sm();
   return dim3((unsigned)(nwork < cap ? nwork : cap));
 }
@@ -691,6 +799,77 @@ void launch_update(const Geom& g, const DevPtrs& d, int vx, bool single, bool pr
       }
     }
   });
+}
+
+// ---- persistent small-mesh loop ---------------------------------------------------------
+template <int VX, int UR>
+static int persistent_max_ctas() {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persistent<VX, UR>, kBX * kBY, 0) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return per_sm * kNumSMs;
+}
+
+bool persistent_plan(const Geom& g, int vx, PersistPlan* out) {
+  const int cap = vx == 2 ? persistent_max_ctas<2, 1>() : persistent_max_ctas<1, 1>();
+  if (cap < kNumSMs) return false;
+  // planes per tile: fewest sequential plane steps per CTA, one extra step per round of tiles
+  int64_t best = -1;
+  PersistPlan p{};
+  for (int zc = 1; zc <= 16; zc *= 2) {
+    if (zc > g.nzl && zc > 1) break;
+    const dim3 tg((g.nx + kBX * vx - 1) / (kBX * vx), (g.ny + kBY - 1) / kBY, (g.nzl + zc - 1) / zc);
+    const int64_t tiles = (int64_t)tg.x * tg.y * tg.z;
+    const int64_t G = tiles < cap ? tiles : cap;
+    const int64_t cost = ((tiles + G - 1) / G) * (zc + 1);
+    if (best < 0 || cost < best) {
+      best = cost;
+      p.tgrid = tg;
+      p.zc = zc;
+      p.grid = (unsigned)G;
+    }
+  }
+  // rows per thread of the update stage: as many loads in flight as still give every CTA work
+  p.ur = 1;
+  for (int ur = 4; ur > 1; ur /= 2) {
+    if (update_nwork(g, vx, ur) >= (int64_t)p.grid) {
+      p.ur = ur;
+      break;
+    }
+  }
+  *out = p;
+  return true;
+}
+
+template <int VX, int UR>
+static cudaError_t launch_persistent_t(const Geom& g, const DevPtrs& d, const PersistPlan& p,
+                                       int max_iters, cudaStream_t s) {
+  Geom gg = g;
+  DevPtrs dd = d;
+  dim3 tgrid = p.tgrid;
+  int zc = p.zc, mi = max_iters;
+  void* args[] = {&gg, &dd, &tgrid, &zc, &mi};
+  return cudaLaunchCooperativeKernel((const void*)k_cg_persistent<VX, UR>, dim3(p.grid),
+                                     dim3(kBX, kBY), args, 0, s);
+}
+
+cudaError_t launch_cg_persistent(const Geom& g, const DevPtrs& d, int vx, const PersistPlan& p,
+                                 int max_iters, cudaStream_t s) {
+  if (vx == 2) {
+    switch (p.ur) {
+      case 4: return launch_persistent_t<2, 4>(g, d, p, max_iters, s);
+      case 2: return launch_persistent_t<2, 2>(g, d, p, max_iters, s);
+      default: return launch_persistent_t<2, 1>(g, d, p, max_iters, s);
+    }
+  }
+  switch (p.ur) {
+    case 4: return launch_persistent_t<1, 4>(g, d, p, max_iters, s);
+    case 2: return launch_persistent_t<1, 2>(g, d, p, max_iters, s);
+    default: return launch_persistent_t<1, 1>(g, d, p, max_iters, s);
+  }
 }
 
 void launch_finish_dir(const DevPtrs& d, cudaStream_t s) { k_finish_dir<<<1, 32, 0, s>>>(d); }

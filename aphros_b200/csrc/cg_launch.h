@@ -35,6 +35,18 @@ void launch_rows_to_soa(const Geom& g, const double* rows, int64_t off, int64_t 
 void launch_soa_to_rows(const Geom& g, const DevPtrs& d, double* rows, cudaStream_t s);
 void launch_jacobi(const Geom& g, const DevPtrs& d, int vx, bool single, cudaStream_t s);
 
+// Persistent small-mesh loop (k_cg_persistent, cg_kernels.cu): one cooperative launch runs
+// iterations until the exit rule fires or max_iters are done.
+struct PersistPlan {
+  dim3 tgrid;     // tiles of the direction stage
+  int zc;         // planes per tile
+  unsigned grid;  // CTAs (all co-resident)
+  int ur;         // rows per thread of the update stage
+};
+bool persistent_plan(const Geom& g, int vx, PersistPlan* out);
+cudaError_t launch_cg_persistent(const Geom& g, const DevPtrs& d, int vx, const PersistPlan& p,
+                                 int max_iters, cudaStream_t s);
+
 // TMA-staged direction+SpMV kernel (cg_spmv_tma.cu)
 struct TmaPlan;  // opaque: tensor maps + launch geometry
 TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen);

@@ -304,6 +304,7 @@ class ModuleLinearConjugateCuda : public ModuleLinear<M> {
     unsigned flags = 0;
     if (!var.Int(key("cuda_graph"), 1)) flags |= APHCG_NO_GRAPH;
     if (!var.Int(key("cuda_tma"), 1)) flags |= APHCG_NO_TMA;
+    if (!var.Int(key("cuda_persistent"), 1)) flags |= APHCG_NO_PERSISTENT;
     // opt-in diagonal preconditioner (NOT SolverConjugate's recurrence; default off)
     if (var.Int(key("jacobi"), 0)) flags |= APHCG_JACOBI_PRECOND;
     return std::make_unique<SolverCuda<M>>(

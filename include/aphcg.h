@@ -50,12 +50,16 @@ enum {
                                 the resident matrix is verified symmetric */
   APHCG_NCCL_REDUCE = 1u << 4, /* multi-GPU: all-reduce the scalars with NCCL instead of
                                 the peer-memory mailboxes (comparison baseline) */
-  APHCG_JACOBI_PRECOND = 1u << 5 /* OPT-IN, not the reference's recurrence: conjugate
+  APHCG_JACOBI_PRECOND = 1u << 5, /* OPT-IN, not the reference's recurrence: conjugate
                                 gradients preconditioned with diag(A) (z = r/e0,
                                 alpha = r.z/p.Ap, beta = r.z_new/r.z, p = z + beta p);
                                 residual and exit rule unchanged (norm of r).  The
                                 reference's SolverConjugate is unpreconditioned, so
                                 iteration counts differ unless diag(A) is constant. */
+  APHCG_NO_PERSISTENT = 1u << 6 /* never run the loop as ONE persistent cooperative kernel.
+                                By default a single-GPU solve whose fields fit in L2 (about
+                                100^3 cells and less) does: same arithmetic, two grid-wide
+                                barriers per iteration instead of two launches. */
 };
 
 typedef struct aphcg aphcg_t;
