@@ -86,6 +86,8 @@ SIGNATURES = {
     "aphcg_get_history": (ctypes.c_int, [_VP, _VP, ctypes.c_int32]),
     "aphcg_run_jacobi": (ctypes.c_int, [_VP, ctypes.POINTER(Conf), ctypes.POINTER(Info)]),
     "aphcg_apply": (ctypes.c_int, [_VP, _VP, _PL, _VP, _PL]),
+    "aphcg_group_assemble_projection": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_double,
+                                                       ctypes.c_double]),
     "aphcg_true_residual": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_double)]),
     "aphcg_group_true_residual": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_double)]),
     "aphcg_assemble_spheres": (ctypes.c_int, [_VP, _VP, ctypes.c_int32, ctypes.c_double,

@@ -118,6 +118,8 @@ struct aphcg {
   bool allow_sym = true;
   int* d_flag = nullptr;
   TmaPlan* tma = nullptr;
+  double* scratch = nullptr;  // grow-only device scratch of the assemblers (inputs staged here)
+  size_t scratch_bytes = 0;
   bool persist = false;   // the loop runs as one persistent cooperative kernel (small meshes)
   PersistPlan pplan{};
   // comm
@@ -389,6 +391,19 @@ int EnsureStage(aphcg_t* h) {
   return 0;
 }
 
+// Grow-only device scratch (the assemblers stage their inputs here): no cudaMalloc/cudaFree
+// pair per call on the per-time-step path.
+int EnsureScratch(aphcg_t* h, size_t bytes) {
+  if (bytes <= h->scratch_bytes) return 0;
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->scratch) CK(cudaFree(h->scratch));
+  h->scratch = nullptr;
+  h->scratch_bytes = 0;
+  CK(cudaMalloc(&h->scratch, bytes));
+  h->scratch_bytes = bytes;
+  return 0;
+}
+
 int WriteState(aphcg_t* h, const aphcg_conf* conf) {
   CgState s{};
   s.tol = conf->tol;
@@ -652,6 +667,7 @@ int aphcg_destroy(aphcg_t* h) {
   cudaFree(h->partials2);
   cudaFree(h->partials3);
   cudaFree(h->rc);
+  cudaFree(h->scratch);
   if (h->h_st) cudaFreeHost(h->h_st);
   for (int b = 0; b < 2; ++b) {
     cudaFree(h->stage[b]);
@@ -930,7 +946,8 @@ int aphcg_assemble_spheres(aphcg_t* h, const double* spheres, int32_t nspheres, 
   if (int rc = SetDevice(h)) return rc;
   double* d_sph = nullptr;
   if (nspheres > 0) {
-    CK(cudaMalloc(&d_sph, sizeof(double) * 4 * (size_t)nspheres));
+    if (int rc = EnsureScratch(h, sizeof(double) * 4 * (size_t)nspheres)) return rc;
+    d_sph = h->scratch;
     CK(cudaMemcpyAsync(d_sph, spheres, sizeof(double) * 4 * (size_t)nspheres,
                        cudaMemcpyHostToDevice, h->stream));
   }
@@ -939,7 +956,6 @@ int aphcg_assemble_spheres(aphcg_t* h, const double* spheres, int32_t nspheres, 
                           h->desc.nz, h->desc.z0, (int)h->desc.nx, (int)h->desc.ny, per, h->stream);
   h->launches += 2;
   cudaError_t e = cudaStreamSynchronize(h->stream);
-  if (d_sph) cudaFree(d_sph);
   if (e != cudaSuccess) return Fail(APHCG_ERR_CUDA, "assemble failed: %s", cudaGetErrorString(e));
   CK(cudaGetLastError());
   h->have_guess = false;
@@ -957,8 +973,8 @@ int aphcg_assemble_projection(aphcg_t* h, const double* rho, const double* vx, c
   const size_t n_vy = (size_t)g.nx * (g.ny + 1) * g.nzl;
   const size_t n_vz = (size_t)g.cz * (g.nzl + 1);
   const size_t n_src = source ? (size_t)g.ncell : 0;
-  double* buf = nullptr;
-  CK(cudaMalloc(&buf, sizeof(double) * (n_rho + n_vx + n_vy + n_vz + n_src)));
+  if (int rc = EnsureScratch(h, sizeof(double) * (n_rho + n_vx + n_vy + n_vz + n_src))) return rc;
+  double* buf = h->scratch;
   double* d_rho = buf;
   double* d_vx = d_rho + n_rho;
   double* d_vy = d_vx + n_vx;
@@ -980,7 +996,6 @@ int aphcg_assemble_projection(aphcg_t* h, const double* rho, const double* vx, c
     h->launches += 2;
     e = cudaStreamSynchronize(h->stream);
   }
-  cudaFree(buf);
   if (e != cudaSuccess) return Fail(APHCG_ERR_CUDA, "assemble failed: %s", cudaGetErrorString(e));
   CK(cudaGetLastError());
   h->have_guess = false;

@@ -302,6 +302,20 @@ int aphcg_group_assemble_spheres(aphcg_group_t* g, const double* spheres, int32_
   });
 }
 
+int aphcg_group_assemble_projection(aphcg_group_t* g, const double* rho, const double* vx,
+                                    const double* vy, const double* vz, const double* source,
+                                    double dt, double hcell) {
+  if (!g || !rho || !vx || !vy || !vz) return GroupFail(APHCG_ERR_ARG, "null argument");
+  const int64_t nx = g->desc.nx, ny = g->desc.ny;
+  return RunAll(g, [&](int q) {
+    const int64_t z0 = g->z0[q];
+    // slab q: density planes z0-1 .. z0+nzl (rank-wide plane -1 is the array's plane 0)
+    return aphcg_assemble_projection(g->h[q], rho + z0 * nx * ny, vx + z0 * (nx + 1) * ny,
+                                     vy + z0 * nx * (ny + 1), vz + z0 * nx * ny,
+                                     source ? source + z0 * nx * ny : nullptr, dt, hcell);
+  });
+}
+
 int aphcg_group_true_residual(aphcg_group_t* g, double* sum_r2) {
   if (!g || !sum_r2) return GroupFail(APHCG_ERR_ARG, "null argument");
   std::vector<double> v(g->n, 0.0);

@@ -97,3 +97,35 @@ def connect(solver, group=None):
     blobs = all_gather_bytes(solver.IpcExport(), group)
     solver.IpcConnect(blobs)
     dist.barrier(group)
+
+
+def bind_to_gpu_numa_node(device: int):
+    """Pins the calling process to the CPUs of the NUMA node its GPU hangs off, so that the
+    pinned staging buffers allocated afterwards (first touch) and the copy-engine traffic stay
+    on that socket: with 8 ranks uploading rows at once, buffers that land on the other
+    socket halve the aggregate host-to-device rate.  Best effort: returns a short description,
+    or None when the topology cannot be read (no sysfs entry, one node, VM)."""
+    import os
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(device), "--query-gpu=pci.bus_id",
+                              "--format=csv,noheader"], capture_output=True, text=True, timeout=20)
+        bus = out.stdout.strip().lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]  # 00000000:1b:00.0 -> 0000:1b:00.0
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return "gpu %d (%s) -> numa node %d, %d cpus" % (device, bus, node, len(allowed))
+    except Exception:
+        return None

@@ -39,6 +39,7 @@
 #include "util/macros.h"
 
 #include "aphcg.h"
+#include "linear_projection.h"
 
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -62,7 +63,7 @@ inline void StreamCopy(double* dst, const double* src, size_t n) {
 }
 
 template <class M>
-class SolverCuda : public Solver<M> {
+class SolverCuda : public Solver<M>, public ProjectionSolver<M> {
  public:
   using Base = Solver<M>;
   using Conf = typename Base::Conf;
@@ -126,6 +127,9 @@ class SolverCuda : public Solver<M> {
       auto& s = *shared_obj_;
       if (s.rows) aphcg_host_free(s.rows);
       if (s.x) aphcg_host_free(s.x);
+      for (double* p : {s.rho, s.vx, s.vy, s.vz, s.src}) {
+        if (p) aphcg_host_free(p);
+      }
       if (s.group) aphcg_group_destroy(s.group);
     }
   }
@@ -218,11 +222,85 @@ class SolverCuda : public Solver<M> {
     return t.info;
   }
 
+  // linear_projection.h: the pressure system of the projection step assembled on the GPU from
+  // the density and the face fluxes (Proj::GetFlux + GetFluxSum, src/solver/proj.ipp:343-383)
+  Info SolveProjection(
+      const FieldCell<Scal>& fc_dens, const FieldFace<Scal>& ff_flux,
+      const FieldCell<Scal>* fc_source, Scal dt, const FieldCell<Scal>* fc_init,
+      FieldCell<Scal>& fc_sol, M& m) override {
+    auto sem = m.GetSem(__func__);
+    struct {
+      Info info;
+    } * ctx(sem);
+    auto& t = *ctx;
+    fassert(dim == 3, "conjugate_cuda: SolveProjection needs a 3-D mesh");
+    fassert(method_ == Method::conjugate, "jacobi_cuda has no SolveProjection");
+    if (sem("alloc") && m.IsLead()) {
+      auto& s = *shared_obj_;
+      if (!s.rho) {
+        const uint64_t nx = s.size[0], ny = s.size[1], nz = s.size[2];
+        auto alloc = [&](double** p, uint64_t n) {
+          Check(aphcg_host_alloc(reinterpret_cast<void**>(p), n * sizeof(double)));
+        };
+        alloc(&s.rho, nx * ny * (nz + 2));
+        alloc(&s.vx, (nx + 1) * ny * nz);
+        alloc(&s.vy, nx * (ny + 1) * nz);
+        alloc(&s.vz, nx * ny * (nz + 1));
+        alloc(&s.src, nx * ny * nz);
+      }
+    }
+    if (sem("bcast")) {
+      m.BcastFromLead(&shared_);
+    }
+    if (sem("gather")) {
+      GatherProjection(fc_dens, ff_flux, fc_source, fc_init, m);
+    }
+    if (sem("solve") && m.IsLead()) {
+      auto& s = *shared_;
+      aphcg_conf conf;
+      conf.tol = this->conf.tol;
+      conf.miniter = this->conf.miniter;
+      conf.maxiter = this->conf.maxiter;
+      aphcg_info info;
+      ++s.ncalls;
+      Check(aphcg_group_assemble_projection(
+          s.group, s.rho, s.vx, s.vy, s.vz, fc_source ? s.src : nullptr, dt,
+          m.GetCellSize()[0]));
+      Check(aphcg_group_upload_guess(s.group, fc_init ? s.x : nullptr, nullptr));
+      Check(aphcg_group_run(s.group, &conf, &info));
+      Check(aphcg_group_download_solution(s.group, s.x, nullptr));
+      s.info.residual = info.residual;
+      s.info.iter = info.iter;
+    }
+    if (sem("scatter")) {
+      auto& s = *shared_;
+      if (!fc_sol.size()) {
+        fc_sol.Reinit(m);
+      }
+      ForEachRow(m, [&](IdxCell c0, size_t i0, size_t n) {
+        std::memcpy(&fc_sol[c0], s.x + i0, n * sizeof(double));
+      });
+      t.info = s.info;
+      m.Comm(&fc_sol, M::CommStencil::direct_one);
+      if (m.flags.linreport && m.IsRoot()) {
+        std::cerr << std::scientific;
+        std::cerr << "linear(conjugate_cuda) 'pressure' (device assembly):"
+                  << " res=" << t.info.residual << " iter=" << t.info.iter << std::endl;
+      }
+    }
+    if (sem()) {
+    }
+    return t.info;
+  }
+
  private:
   struct Shared {
     aphcg_group_t* group = nullptr;  // one slab per GPU; a group of one is the plain solver
     double* rows = nullptr;  // pinned, rank-wide, [nz][ny][nx][8]
     double* x = nullptr;     // pinned, rank-wide, guess in / solution out
+    // SolveProjection only (allocated on first use): rank-wide density with one ghost plane
+    // below and above, face fluxes, source
+    double *rho = nullptr, *vx = nullptr, *vy = nullptr, *vz = nullptr, *src = nullptr;
     MIdx origin;
     size_t size[3] = {1, 1, 1};  // rank-wide inner cells; 1 in the directions a mesh lacks
     Info info;
@@ -234,6 +312,34 @@ class SolverCuda : public Solver<M> {
       return i;
     }
   };
+  // This block's part of the rank-wide inputs of aphcg_group_assemble_projection.  Every
+  // location is written by exactly one block: a cell's density and LOWER faces by the block
+  // that owns the cell, the domain's last upper faces by the block that touches that boundary.
+  void GatherProjection(
+      const FieldCell<Scal>& fc_dens, const FieldFace<Scal>& ff_flux,
+      const FieldCell<Scal>* fc_source, const FieldCell<Scal>* fc_init, const M& m) const {
+    auto& s = *shared_;
+    const size_t nx = s.size[0], ny = s.size[1], nz = s.size[2];
+    const bool perz = m.flags.is_periodic[dim - 1];
+    const auto& ic = m.GetIndexCells();
+    for (auto c : m.Cells()) {
+      const MIdx w = ic.GetMIdx(c) - s.origin;
+      const size_t i = w[0], j = w[1], k = dim > 2 ? w[dim - 1] : 0;
+      const size_t cell = (k * ny + j) * nx + i;
+      const Scal rho = fc_dens[c];
+      s.rho[cell + nx * ny] = rho;  // plane k+1 of the ghost-extended array
+      if (k == 0) s.rho[(perz ? nz + 1 : 0) * nx * ny + j * nx + i] = rho;
+      if (k == nz - 1) s.rho[(perz ? 0 : nz + 1) * nx * ny + j * nx + i] = rho;
+      s.src[cell] = fc_source ? (*fc_source)[c] : 0.;
+      s.x[cell] = fc_init ? (*fc_init)[c] : 0.;
+      s.vx[(k * ny + j) * (nx + 1) + i] = ff_flux[m.GetFace(c, IdxNci(0))];
+      if (i == nx - 1) s.vx[(k * ny + j) * (nx + 1) + nx] = ff_flux[m.GetFace(c, IdxNci(1))];
+      s.vy[(k * (ny + 1) + j) * nx + i] = ff_flux[m.GetFace(c, IdxNci(2))];
+      if (j == ny - 1) s.vy[(k * (ny + 1) + ny) * nx + i] = ff_flux[m.GetFace(c, IdxNci(3))];
+      s.vz[cell] = ff_flux[m.GetFace(c, IdxNci(4))];
+      if (k == nz - 1) s.vz[cell + nx * ny] = ff_flux[m.GetFace(c, IdxNci(5))];
+    }
+  }
   // f(first cell of the row, its index in the rank-wide arrays, cells in the row) for every
   // x-row of the block's inner cells
   template <class F>

@@ -239,6 +239,13 @@ int aphcg_group_assemble_spheres(
     double dt);
 /* sum over ALL slabs (added in slab order) */
 int aphcg_group_true_residual(aphcg_group_t* g, double* sum_r2);
+/* aphcg_assemble_projection for the group.  Arrays are RANK-WIDE and compact:
+ * rho (nz+2, ny, nx) with one ghost plane below and above the domain (the periodic image, or
+ * anything finite at a wall), vx (nz, ny, nx+1), vy (nz, ny+1, nx), vz (nz+1, ny, nx),
+ * source (nz, ny, nx) or NULL. */
+int aphcg_group_assemble_projection(
+    aphcg_group_t* g, const double* rho, const double* vx, const double* vy, const double* vz,
+    const double* source, double dt, double hcell);
 
 /* Device-side timing on the handle's stream (CUDA events): start records an
  * event; stop records another, waits for it and returns the milliseconds between. */

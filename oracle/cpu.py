@@ -128,12 +128,17 @@ def have_reference_assembler():
 
 
 def assemble_reference(rho, vx, vy, vz, source=None, *, dt=1e-3, periodic=(False, False, False),
-                       block=None):
+                       block=None, plugin=None, solver="conjugate_cuda", tol=1e-8, maxiter=1000,
+                       threads=1, env=None):
     """Rows of the projection pressure system assembled by the reference's own functions
     (oracle/_ref/ref_assemble: InterpolateHarmonic, GradientImplicit, AppendExpr in the
     sequence of Proj::GetFlux/GetFluxSum, src/solver/proj.ipp:343-383) from a cell density
     (nz,ny,nx) and face volume fluxes vx (nz,ny,nx+1), vy (nz,ny+1,nx), vz (nz+1,ny,nx).
-    Mesh extent 1 (h = 1/max(n)); non-periodic domain faces are walls.  Returns (nz,ny,nx,8)."""
+    Mesh extent 1 (h = 1/max(n)); non-periodic domain faces are walls.  Returns (nz,ny,nx,8).
+
+    With `plugin` (the adapter .so) the module `solver` is also asked for the
+    linear::ProjectionSolver capability and solves the same projection from the same fields,
+    zero guess: returns (rows, x, iter, residual)."""
     rho = np.ascontiguousarray(rho, dtype=np.float64)
     nz, ny, nx = rho.shape
     b = block if block is not None else (nx, ny, nz)
@@ -158,11 +163,22 @@ def assemble_reference(rho, vx, vy, vz, source=None, *, dt=1e-3, periodic=(False
                "--pz", str(int(periodic[2])), "--out", out]
         for name, path in files.items():
             cmd += ["--" + name, path]
-        p = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True,
-                           env=dict(os.environ, OMP_NUM_THREADS="1"))
+        xout = os.path.join(tmp, "x.f64")
+        if plugin:
+            cmd += ["--plugin", plugin, "--solver", solver, "--xout", xout, "--tol", repr(float(tol)),
+                    "--maxiter", str(maxiter)]
+        e = dict(os.environ, OMP_NUM_THREADS=str(threads))
+        e.update(env or {})
+        p = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, env=e)
         if p.returncode != 0:
             raise RuntimeError("ref_assemble failed:\n" + p.stdout + p.stderr)
-        return np.fromfile(out, dtype=np.float64).reshape(nz, ny, nx, 8)
+        rows = np.fromfile(out, dtype=np.float64).reshape(nz, ny, nx, 8)
+        if not plugin:
+            return rows
+        x = np.fromfile(xout, dtype=np.float64).reshape(nz, ny, nx)
+        with open(xout + ".info") as f:
+            it, res = f.read().split()
+        return rows, x, int(it), float(res)
 
 
 def have_reference():

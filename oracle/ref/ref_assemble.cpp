@@ -24,11 +24,21 @@
 //   --vy   nx*(ny+1)*nz      y faces;   --vz  nx*ny*(nz+1)  z faces
 //   --src  nx*ny*nz          volume source (optional)
 //   --out  nx*ny*nz*8        rows [c, x-, x+, y-, y+, z-, z+, const]
+//
+// With `--plugin LIB.so --solver NAME --xout FILE` the module NAME (loaded from LIB.so like
+// ref_cg does) is additionally asked for the linear::ProjectionSolver capability
+// (aphros_b200/plugin/linear_projection.h) and solves the SAME projection from the same
+// density / flux / source fields, zero guess; its solution goes to FILE (+ FILE.info with
+// "iter residual").  That is the caller-side code a maintainer would put into
+// Proj::Project, exercised through the reference's own mesh and coroutine machinery.
 
+#include <dlfcn.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -37,6 +47,8 @@
 #include "solver/approx_eb.h"
 #include "solver/embed.h"
 #include "util/distr.h"
+
+#include "../../aphros_b200/plugin/linear_projection.h"
 
 using M = MeshCartesian<double, 3>;
 using Scal = typename M::Scal;
@@ -48,9 +60,12 @@ using UEB = UEmbed<M>;
 namespace {
 
 struct Global {
-  std::vector<double> rho, v[3], src, rows;
+  std::vector<double> rho, v[3], src, rows, x;
   long n[3] = {0, 0, 0};
   double dt = 1;
+  std::string solver;  // module asked for the ProjectionSolver capability ("" = none)
+  int iter = 0;
+  double residual = 0;
 } g;
 
 std::vector<double> ReadRaw(const std::string& path, size_t count) {
@@ -65,11 +80,16 @@ std::vector<double> ReadRaw(const std::string& path, size_t count) {
   return v;
 }
 
-void Run(M& m, Vars&) {
+void Run(M& m, Vars& var) {
   auto sem = m.GetSem(__func__);
   struct {
     FieldCell<Scal> fcr;
     FieldCell<Scal> fcsv;
+    FieldFace<Scal> ffv;
+    FieldCell<Scal> fcp;
+    std::unique_ptr<linear::Solver<M>> solver;
+    linear::ProjectionSolver<M>* proj = nullptr;
+    typename linear::Solver<M>::Info info;
   } * ctx(sem);
   auto& t = *ctx;
   auto cidx = [&](MIdx w) -> size_t {
@@ -88,7 +108,8 @@ void Run(M& m, Vars&) {
   if (sem("assemble")) {
     const MIdx gs = m.GetGlobalSize();
     // volume fluxes
-    FieldFace<Scal> ffv(m, 0);
+    auto& ffv = t.ffv;
+    ffv.Reinit(m, 0);
     for (auto f : m.Faces()) {
       const MIdx w = m.GetIndexFaces().GetMIdx(f);
       const size_t d = m.GetIndexFaces().GetDir(f).raw();
@@ -122,6 +143,29 @@ void Run(M& m, Vars&) {
       sum.back() -= t.fcsv[c] * m.GetVolume(c);
       const size_t i = cidx(m.GetIndexCells().GetMIdx(c));
       for (size_t k = 0; k < 8; ++k) g.rows[i * 8 + k] = sum[k];
+    }
+  }
+  if (!g.solver.empty()) {
+    if (sem("make")) {
+      auto factory = linear::ModuleLinear<M>::GetInstance(g.solver);
+      fassert(factory, "Solver not found: " + g.solver);
+      t.solver = factory->Make(var, "symm", m);
+      t.proj = dynamic_cast<linear::ProjectionSolver<M>*>(t.solver.get());
+      fassert(t.proj, "module " + g.solver + " does not implement linear::ProjectionSolver");
+      t.fcp.Reinit(m, 0);
+    }
+    if (sem.Nested("solve")) {
+      t.info = t.proj->SolveProjection(
+          t.fcr, t.ffv, g.src.empty() ? nullptr : &t.fcsv, g.dt, nullptr, t.fcp, m);
+    }
+    if (sem("store")) {
+      for (auto c : m.Cells()) {
+        g.x[cidx(m.GetIndexCells().GetMIdx(c))] = t.fcp[c];
+      }
+      if (m.IsRoot()) {
+        g.iter = t.info.iter;
+        g.residual = t.info.residual;
+      }
     }
   }
   if (sem()) {
@@ -166,6 +210,15 @@ int main(int argc, const char** argv) {
   if (src[0]) g.src = ReadRaw(src, n);
   g.dt = atof(Arg(argc, argv, "--dt", "1"));
   g.rows.assign(n * 8, 0.);
+  const char* plugin = Arg(argc, argv, "--plugin", "");
+  if (plugin[0]) {
+    if (!dlopen(plugin, RTLD_NOW | RTLD_GLOBAL)) {
+      std::cerr << "ref_assemble: dlopen failed: " << dlerror() << std::endl;
+      return 2;
+    }
+    g.solver = Arg(argc, argv, "--solver", "conjugate_cuda");
+    g.x.assign(n, 0.);
+  }
 
   std::stringstream conf;
   conf << "set int bsx " << bs[0] << "\nset int bsy " << bs[1] << "\nset int bsz "
@@ -177,6 +230,9 @@ int main(int argc, const char** argv) {
   conf << "set int hypre_periodic_y " << Arg(argc, argv, "--py", "0") << "\n";
   conf << "set int hypre_periodic_z " << Arg(argc, argv, "--pz", "0") << "\n";
   conf << "set string backend native\nset double extent 1\nset int VERBOSE 0\n";
+  conf << "set double hypre_symm_tol " << Arg(argc, argv, "--tol", "1e-8") << "\n";
+  conf << "set int hypre_symm_maxiter " << Arg(argc, argv, "--maxiter", "1000") << "\n";
+  conf << Arg(argc, argv, "--extra", "") << "\n";
 
   MpiWrapper mpi(&argc, &argv);
   const int rc = RunMpiBasicString<M>(mpi, Run, conf.str());
@@ -184,5 +240,14 @@ int main(int argc, const char** argv) {
   FILE* f = fopen(Arg(argc, argv, "--out", "rows.f64"), "wb");
   fwrite(g.rows.data(), sizeof(double), g.rows.size(), f);
   fclose(f);
+  if (!g.solver.empty()) {
+    const std::string xout = Arg(argc, argv, "--xout", "x.f64");
+    f = fopen(xout.c_str(), "wb");
+    fwrite(g.x.data(), sizeof(double), g.x.size(), f);
+    fclose(f);
+    std::ofstream info(xout + ".info");
+    info.precision(17);
+    info << g.iter << " " << g.residual << "\n";
+  }
   return 0;
 }

@@ -151,6 +151,66 @@ int aphcg_group_upload_guess(aphcg_group_t* g, const double* x0, const aphcg_lay
   return 0;
 }
 
+/* Rows from density + face fluxes in the reference's order of operations (what
+ * aphcg_assemble_projection computes on the device; aphros_b200/systems.py:projection_rows). */
+int aphcg_group_assemble_projection(aphcg_group_t* g, const double* rho, const double* vx,
+                                    const double* vy, const double* vz, const double* source,
+                                    double dt, double hcell) {
+  const long nx = g->desc.nx, ny = g->desc.ny, nz = g->desc.nz;
+  const double vol = g->desc.cell_volume, inv_h = 1.0 / hcell, area = vol / hcell;
+  free(g->rows);
+  g->rows = (double*)malloc(sizeof(double) * 8 * ncell(g));
+  for (long k = 0; k < nz; ++k)
+    for (long j = 0; j < ny; ++j)
+      for (long i = 0; i < nx; ++i) {
+        const long nn[3] = {nx, ny, nz}, w[3] = {i, j, k};
+        double* e = g->rows + 8 * ((k * ny + j) * nx + i);
+        const double inv_c = 1.0 / rho[((k + 1) * ny + j) * nx + i];
+        double diag = 0.0;
+        for (int q = 0; q < 6; ++q) {
+          const int d = q / 2, up = q % 2;
+          long v[3] = {i, j, k};
+          v[d] += up ? 1 : -1;
+          const int outside = v[d] < 0 || v[d] >= nn[d];
+          double a = 0.0;
+          if (!(outside && !g->desc.periodic[d])) {
+            if (d < 2) v[d] = (v[d] + nn[d]) % nn[d]; /* z: the ghost planes hold the images */
+            const double inv_n = 1.0 / rho[((v[2] + 1) * ny + v[1]) * nx + v[0]];
+            const double rf = 1.0 / ((inv_c + inv_n) * 0.5);
+            a = inv_h * ((area / rf) * dt);
+          }
+          (void)w;
+          e[1 + q] = -a;
+          diag = diag + a;
+        }
+        e[0] = diag;
+        double e7 = -vx[(k * ny + j) * (nx + 1) + i] + vx[(k * ny + j) * (nx + 1) + i + 1];
+        e7 = e7 - vy[(k * (ny + 1) + j) * nx + i];
+        e7 = e7 + vy[(k * (ny + 1) + j + 1) * nx + i];
+        e7 = e7 - vz[(k * ny + j) * nx + i];
+        e7 = e7 + vz[((k + 1) * ny + j) * nx + i];
+        e7 = e7 - (source ? source[(k * ny + j) * nx + i] : 0.0) * vol;
+        e[7] = e7;
+      }
+  logf_("assemble_projection dt=%.17g h=%.17g source=%d", dt, hcell, source ? 1 : 0);
+  return 0;
+}
+
+int aphcg_group_run(aphcg_group_t* g, const aphcg_conf* conf, aphcg_info* info) {
+  if (!g->rows) return APHCG_ERR_STATE;
+  const cg_oracle_desc d = odesc(g, conf);
+  free(g->x);
+  g->x = (double*)malloc(sizeof(double) * ncell(g));
+  double res = 0;
+  int it = 0;
+  const int rc = cg_oracle_conjugate(&d, g->rows, g->x0, g->x, &res, &it, NULL);
+  logf_("run tol=%.17g maxiter=%d -> iter=%d residual=%.17g", conf->tol, conf->maxiter, it, res);
+  memset(info, 0, sizeof(*info));
+  info->residual = res;
+  info->iter = it;
+  return rc;
+}
+
 int aphcg_group_run_jacobi(aphcg_group_t* g, const aphcg_conf* conf, aphcg_info* info) {
   if (!g->rows) return APHCG_ERR_STATE;
   const cg_oracle_desc d = odesc(g, conf);

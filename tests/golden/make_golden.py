@@ -160,6 +160,24 @@ def build_assembly_case(name):
     return dict(rho=rho, vx=vx, vy=vy, vz=vz, source=src, dt=1e-3, periodic=per, block=block)
 
 
+def consistent_projection_case(name):
+    """like build_assembly_case, but a system CG can solve: moderate density variation, no
+    source, zero flux through walls -- the right-hand side then sums to zero (telescoping), as
+    the singular Neumann / periodic problem requires"""
+    c = build_assembly_case(name)
+    rng = np.random.default_rng(99)
+    c["rho"] = np.exp(0.5 * rng.standard_normal(c["rho"].shape))
+    per = c["periodic"]
+    if not per[0]:
+        c["vx"][:, :, 0] = c["vx"][:, :, -1] = 0.0
+    if not per[1]:
+        c["vy"][:, 0, :] = c["vy"][:, -1, :] = 0.0
+    if not per[2]:
+        c["vz"][0] = c["vz"][-1] = 0.0
+    c["source"] = None
+    return c
+
+
 def main_assembly():
     assert cpu.have_reference_assembler(), "build oracle/_ref first: make -C oracle/ref app"
     for name in ASSEMBLY_CASES:

@@ -14,6 +14,7 @@ from __future__ import annotations
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -70,6 +71,37 @@ def test_gather_scatter_over_blocks(fake, tmp_path, backend, block, threads):
     assert sum(l.startswith("solve") for l in log) == 1 and log[-1] == "destroy"
     # (the driver always passes an fc_init field, zero when no guess is given)
     assert "tol=1.0000000000000001e-09 miniter=0 maxiter=2000" in [l for l in log if l.startswith("solve")][0]
+
+
+@pytest.mark.parametrize("name,threads", [("assemble_walls32", 1), ("assemble_perz32_b16", 4),
+                                          ("assemble_perxz_ragged", 1)])
+def test_projection_entry_gathers_density_and_fluxes(fake, tmp_path, name, threads):
+    """linear::ProjectionSolver (aphros_b200/plugin/linear_projection.h) over the test double:
+    the adapter gathers the blocks' density (with its z ghost planes), face fluxes and source
+    into the rank-wide arrays of aphcg_group_assemble_projection; the double assembles rows
+    from exactly those arrays, and the solve must be the reference's own for the rows the
+    reference's assembler builds from the same fields (one block, 8 blocks with OpenMP,
+    periodic x/z on a ragged mesh)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    from oracle import cpu
+    if not cpu.have_reference_assembler():
+        pytest.skip("oracle/_ref/ref_assemble not present")
+    c = make_golden.consistent_projection_case(name)
+    log = str(tmp_path / "log_proj.txt")
+    kw = dict(tol=1e-9, maxiter=3000)
+    rows, x, it, res = cpu.assemble_reference(
+        c["rho"], c["vx"], c["vy"], c["vz"], c["source"], dt=c["dt"], periodic=c["periodic"],
+        block=c["block"], plugin=PLUGIN, threads=threads,
+        env={"LD_PRELOAD": fake, "FAKE_APHCG_LOG": log}, **kw)
+    xr, itr, resr, _ = cpu.solve_reference(rows, periodic=c["periodic"], block=c["block"],
+                                           solver="conjugate", **kw)
+    assert itr < 3000 and abs(it - itr) <= 2 + itr // 100 and res < 1e-9
+    assert rel_max_abs(x, xr) <= 1e-7
+    lines = open(log).read().splitlines()
+    assert any(l.startswith("assemble_projection dt=0.001") and "source=0" in l for l in lines)
+    assert [l.split()[0] for l in lines if not l.startswith("create")] == [
+        "assemble_projection", "upload_guess", "run", "download_solution", "destroy"]
 
 
 def test_guess_walls_maxnorm_and_ragged_mesh(fake, tmp_path):
