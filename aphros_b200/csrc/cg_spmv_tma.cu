@@ -31,14 +31,18 @@ constexpr int TY = 8;     // tile rows
 constexpr int S = 3;      // TMA stages in flight
 constexpr int RING = 4;   // p_new planes kept
 
-// Tile configuration: TX cells along x, TX/2 lanes x 4 row-pairs = 2*TX threads.
-//   TX=128: 256 threads, 104 KB shared memory, 2 CTAs per SM
+// Tile configuration: TX cells along x, TX/2 lanes x (TY / RPT) thread rows; a thread owns a
+// pair of cells in RPT consecutive rows.
+//   TX=128, RPT=2: 256 threads, 104 KB shared memory, 2 CTAs per SM, <= 128 registers
+//   TX=128, RPT=1: 512 threads, same tile: twice the warps per SM (32) to hide the latency of
+//                  the coefficient streams, at <= 64 registers per thread (APHCG_RPT=1)
 //   TX=64 : 128 threads,  54 KB shared memory, 4 CTAs per SM (more independent
 //           phases per SM to overlap one CTA's barrier/compute with another's loads)
-template <int TX_>
+template <int TX_, int RPT_ = 2>
 struct Cfg {
   static constexpr int TX = TX_;
-  static constexpr int NT = 2 * TX;
+  static constexpr int RPT = RPT_;
+  static constexpr int NT = TX * TY / (2 * RPT);
   static constexpr int LXN = TX / 2;  // threads along x
   static constexpr int MINB = TX == 128 ? 2 : 4;
   static constexpr int BW = TX + 4;   // box width: x0-2 .. x0+TX+1 (inner pairs 16-byte aligned)
@@ -101,13 +105,13 @@ __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
 // all loads of a step back to back and their latency overlaps the p_new phase
 // (profiles/r01d_dir_spmv_stalls_by_line.md: 22 % of the stall samples sit on those consumers).
 // Same values into the same FMAs.
-template <int TXT, bool kSingle, bool kSym, bool kDefer = false>
-__global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
+template <int TXT, bool kSingle, bool kSym, bool kDefer = false, int RPT = 2>
+__global__ void __launch_bounds__(Cfg<TXT, RPT>::NT, Cfg<TXT, RPT>::MINB)
     k_dir_spmv_tma(const Geom g, const DevPtrs d, const int zc, const int pd, const int opts,
                    const __grid_constant__ CUtensorMap map_r,
                    const __grid_constant__ CUtensorMap map_p0,
                    const __grid_constant__ CUtensorMap map_p1) {
-  using C = Cfg<TXT>;
+  using C = Cfg<TXT, RPT>;
   constexpr int TX = C::TX, NT = C::NT, BW = C::BW, BOX = C::BOX, BOXB = C::BOXB;
   // Dynamic shared memory, indexed only through pointers derived from the
   // __shared__ symbol itself so that every access compiles to LDS/STS (a detour
@@ -162,16 +166,16 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
     for (int n = 0; n < S && n < np; ++n) issue(n);
   }
 
-  // cells of this thread: pair (2*lx, 2*lx+1) in rows 2*ly and 2*ly+1 of the tile
+  // cells of this thread: pair (2*lx, 2*lx+1) in rows RPT*ly .. RPT*ly+RPT-1 of the tile
   const int lx = tid % C::LXN, ly = tid / C::LXN;
   const int lane = tid & 31;
   const int ci = x0 + 2 * lx;
   const bool act_x = ci < g.nx;
-  bool act[2];
-  int cj[2];
+  bool act[RPT];
+  int cj[RPT];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    cj[h] = y0 + 2 * ly + h;
+  for (int h = 0; h < RPT; ++h) {
+    cj[h] = y0 + RPT * ly + h;
     act[h] = act_x && cj[h] < g.ny;
   }
   // ownership of box columns/rows for the p_new stores (interior + face ghosts)
@@ -181,10 +185,13 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
   const int own_yhi = min(y0 + TY, g.ny) + (y0 + TY >= g.ny ? 1 : 0);
 
   double acc = 0.0;
-  Vec<2> zcarry[2];
-  zcarry[0].v[0] = zcarry[0].v[1] = zcarry[1].v[0] = zcarry[1].v[1] = 0.0;
-  Vec<2> p2n[2];
-  p2n[0] = p2n[1] = zcarry[0];
+  Vec<2> zcarry[RPT];
+  Vec<2> p2n[RPT];
+#pragma unroll
+  for (int h = 0; h < RPT; ++h) {
+    zcarry[h].v[0] = zcarry[h].v[1] = 0.0;
+    p2n[h] = zcarry[h];
+  }
   for (int n = 0; n < np; ++n) {
     const int z = k0 - 1 + n;  // plane whose p_new is formed in this step
     const int m = z - 1;       // plane whose stencil is evaluated in this step
@@ -220,11 +227,11 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
     }
 
     // -- issue the read-once streams of this step before any waiting ---------------
-    Vec<2> a[2][7];
-    Vec<2> uu[2];
+    Vec<2> a[RPT][7];
+    Vec<2> uu[RPT];
     if constexpr (!kSym) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < RPT; ++h) {
         if (do_stencil && act[h]) {
           const int64_t idc = ci + cj[h] * g.cy + (int64_t)m * g.cz;
 #pragma unroll
@@ -236,10 +243,11 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
       // a[h][2], a[h][4], a[h][6] <- lower coefficients of the upper neighbours
       Vec<2> zero2;
       zero2.v[0] = zero2.v[1] = 0.0;
-      a[0][1] = a[1][1] = zero2;
+#pragma unroll
+      for (int h = 0; h < RPT; ++h) a[h][1] = zero2;
       if (do_stencil) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < RPT; ++h) {
           if (act[h]) {
             const int64_t idc = ci + cj[h] * g.cy + (int64_t)m * g.cz;
             a[h][0] = ldv_stream<2>(d.a[0] + idc);
@@ -268,7 +276,7 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
         }
         // x+ of the second cell of the pair = x- of the next lane's first cell
 #pragma unroll
-        for (int h = 0; h < 2 && !kDefer; ++h) {
+        for (int h = 0; h < RPT && !kDefer; ++h) {
           const double from_next = __shfl_down_sync(0xffffffffu, a[h][1].v[0], 1);
           if (act[h]) {
             const int64_t idc = ci + cj[h] * g.cy + (int64_t)m * g.cz;
@@ -285,16 +293,16 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
       }
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < RPT; ++h) {
       if (z_inner && xmode != 0 && act[h]) {
         uu[h] = ldv_stream<2>(d.u + ci + cj[h] * g.cy + (int64_t)z * g.cz);
       }
     }
     // p_{k-2} of plane z+1, consumed in the NEXT step: the __syncthreads that ends this step
     // orders the load before any thread of the CTA overwrites those cells with p_new(z+1)
-    Vec<2> p2c[2];
+    Vec<2> p2c[RPT];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < RPT; ++h) {
       p2c[h] = p2n[h];
       if (xmode == 2 && z + 1 >= k0 && z + 1 < k1 && act[h]) {
         p2n[h] = ldv_stream<2>(pn_glob + g.poff + ci + (int64_t)cj[h] * g.py + (int64_t)(z + 1) * g.pz);
@@ -340,9 +348,9 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
     // -- (b) deferred x update (linear.ipp:88) with p_old of the own cells -------------
     if (z_inner && xmode != 0) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < RPT; ++h) {
         if (act[h]) {
-          const int o = (2 * ly + h + 1) * BW + 2 + 2 * lx;
+          const int o = (RPT * ly + h + 1) * BW + 2 + 2 * lx;
           const double2 pv = *reinterpret_cast<const double2*>(sp + o);
           if (xmode == 2) {  // the older update first: same FMAs, same order as one per iteration
             uu[h].v[0] = fma(alpha_prev2, p2c[h].v[0], uu[h].v[0]);
@@ -365,19 +373,19 @@ __global__ void __launch_bounds__(Cfg<TXT>::NT, Cfg<TXT>::MINB)
       if constexpr (kSym && kDefer) {
         // the consumers of this step's coefficient loads, deferred to here (see kDefer)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < RPT; ++h) {
           const double from_next = __shfl_down_sync(0xffffffffu, a[h][1].v[0], 1);
           if (act[h]) {
-            if (h == 1) a[1][3] = a[0][4];
+            if (h == 1) a[h][3] = a[0][4];
             a[h][2].v[0] = a[h][1].v[1];
             if (ci + 2 < g.nx && lane != 31) a[h][2].v[1] = from_next;
           }
         }
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < RPT; ++h) {
         if (act[h]) {
-          const int o = (2 * ly + h + 1) * BW + 2 + 2 * lx;
+          const int o = (RPT * ly + h + 1) * BW + 2 + 2 * lx;
           const double2 pc = *reinterpret_cast<const double2*>(rc + o);
           const double pxm = rc[o - 1], pxp = rc[o + 2];
           const double2 pym = *reinterpret_cast<const double2*>(rc + o - BW);
@@ -435,6 +443,7 @@ struct TmaPlan {
   int pd;  // L2 prefetch distance in planes (0 = off)
   int opts;  // bit 0: streaming stores of p_new; bit 1: kDefer variant of the symmetric kernel
   int tx;  // tile width in use (64 or 128)
+  int rpt;  // rows per thread: 2, or 1 (512-thread CTAs; 128-wide tiles, symmetric storage only)
 };
 
 template <int TXT>
@@ -451,6 +460,10 @@ static bool set_smem_limit() {
          cudaFuncSetAttribute(k_dir_spmv_tma<TXT, true, true, true>,
                               cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess &&
          cudaFuncSetAttribute(k_dir_spmv_tma<TXT, false, true, true>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess &&
+         cudaFuncSetAttribute(k_dir_spmv_tma<TXT, true, true, false, 1>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess &&
+         cudaFuncSetAttribute(k_dir_spmv_tma<TXT, false, true, false, 1>,
                               cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) == cudaSuccess;
 }
 
@@ -524,6 +537,10 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
   p->opts = 1;  // streaming p_new stores: 1.87 vs 1.90 ms at 512^3
   if (const char* eo = getenv("APHCG_PSTREAM")) p->opts = atoi(eo) ? 1 : 0;
   if (const char* ed = getenv("APHCG_DEFER")) p->opts |= atoi(ed) ? 2 : 0;
+  // one row pair per thread: 512-thread CTAs, twice the warps per SM at <= 64 registers.
+  // Measured round 2 (profiles/r02_rows_per_thread_sweep.txt): 1.83-1.85 vs 1.89 ms at 512^3.
+  p->rpt = 1;
+  if (const char* er = getenv("APHCG_RPT")) p->rpt = atoi(er) == 2 ? 2 : 1;
   p->grid = dim3((g.nx + TX - 1) / TX, (g.ny + TY - 1) / TY, (g.nzl + zc - 1) / zc);
   if (!(TX == 64 ? set_smem_limit<64>() : set_smem_limit<128>())) {
     cudaGetLastError();
@@ -536,9 +553,9 @@ TmaPlan* tma_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen)
 void tma_plan_destroy(TmaPlan* p) { delete p; }
 unsigned tma_plan_blocks(const TmaPlan* p) { return p->grid.x * p->grid.y * p->grid.z; }
 void tma_plan_describe(const TmaPlan* p, char* buf, int buflen) {
-  snprintf(buf, buflen, "tile=%dx%d planes_per_cta=%d stages=%d l2_prefetch=%d pstream=%d%s ctas=%u",
+  snprintf(buf, buflen, "tile=%dx%d planes_per_cta=%d stages=%d l2_prefetch=%d pstream=%d%s%s ctas=%u",
            p->tx, TY, p->zc, S, p->pd, p->opts & 1, (p->opts & 2) ? " defer=1" : "",
-           tma_plan_blocks(p));
+           p->rpt == 1 ? " rows_per_thread=1" : "", tma_plan_blocks(p));
 }
 
 template <int TXT>
@@ -549,6 +566,17 @@ static void launch_cfg(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool s
   k_dir_spmv_tma<TXT, SINGLE, SYM, DEFER><<<p->grid, C::NT, C::kSmemBytes, s>>>(                  \
       g, d, p->zc, p->pd, p->opts, p->map_r, p->map_p0, p->map_p1)
   const bool defer = sym && (p->opts & 2) != 0;
+  if (sym && !defer && p->rpt == 1) {
+    using C1 = Cfg<TXT, 1>;
+    if (single) {
+      k_dir_spmv_tma<TXT, true, true, false, 1><<<p->grid, C1::NT, C1::kSmemBytes, s>>>(
+          g, d, p->zc, p->pd, p->opts, p->map_r, p->map_p0, p->map_p1);
+    } else {
+      k_dir_spmv_tma<TXT, false, true, false, 1><<<p->grid, C1::NT, C1::kSmemBytes, s>>>(
+          g, d, p->zc, p->pd, p->opts, p->map_r, p->map_p0, p->map_p1);
+    }
+    return;
+  }
   if (single) {
     if (defer) APHCG_LAUNCH_TMA(true, true, true);
     else if (sym) APHCG_LAUNCH_TMA(true, true, false);
