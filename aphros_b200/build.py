@@ -10,8 +10,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libaphcg.so")
-SOURCES = ["aphcg.cu", "aphcg_group.cu", "cg_kernels.cu", "cg_spmv_tma.cu", "cg_assemble.cu"]
-HEADERS = ["cg_types.h", "cg_kernels.cuh", "cg_launch.h", "cg_group.h", "nccl_dl.h",
+SOURCES = ["aphcg.cu", "aphcg_group.cu", "cg_kernels.cu", "cg_spmv_tma.cu", "cg_spmv_tma2.cu",
+           "cg_assemble.cu"]
+HEADERS = ["cg_types.h", "cg_kernels.cuh", "cg_launch.h", "cg_group.h", "nccl_dl.h", "cg_tma.cuh",
            os.path.join("..", "..", "include", "aphcg.h")]
 
 

@@ -24,6 +24,7 @@ APHCG_NO_SYM = 1 << 3
 APHCG_NCCL_REDUCE = 1 << 4
 APHCG_JACOBI_PRECOND = 1 << 5
 APHCG_NO_PERSISTENT = 1 << 6
+APHCG_NO_STREAM = 1 << 7
 UNIQUE_ID_BYTES = 128
 IPC_BYTES = 128
 

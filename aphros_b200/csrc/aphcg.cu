@@ -118,6 +118,7 @@ struct aphcg {
   bool allow_sym = true;
   int* d_flag = nullptr;
   TmaPlan* tma = nullptr;
+  Tma2Plan* tma2 = nullptr;  // all-operands-by-TMA variant (symmetric storage only)
   double* scratch = nullptr;  // grow-only device scratch of the assemblers (inputs staged here)
   size_t scratch_bytes = 0;
   bool persist = false;   // the loop runs as one persistent cooperative kernel (small meshes)
@@ -200,7 +201,9 @@ int AllReduce(aphcg_t* h, double* p, ncclRedOp_t op) {
 
 // One CG iteration enqueued on h->stream.
 int EnqueueIteration(aphcg_t* h) {
-  if (h->use_tma) {
+  if (h->use_tma && h->tma2 && h->sym) {
+    launch_dir_spmv_stream(h->tma2, h->g, h->d, h->single, h->stream);
+  } else if (h->use_tma) {
     launch_dir_spmv_tma(h->tma, h->g, h->d, h->single, h->sym, h->stream);
   } else {
     launch_dir_spmv_plain(h->g, h->d, h->vx, h->single, h->stream);
@@ -612,6 +615,14 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
     if (h->tma) {
       h->use_tma = true;
       h->nslots = std::max(h->nslots, tma_plan_blocks(h->tma));
+      // symmetric storage: the variant with every operand staged by TMA (cg_spmv_tma2.cu),
+      // 1.60 vs 1.84 ms at 512^3; APHCG_STREAM=0 / APHCG_NO_STREAM keep the LDG-fed kernel
+      bool want2 = !(ds.flags & APHCG_NO_STREAM);
+      if (const char* e2 = getenv("APHCG_STREAM")) want2 = atoi(e2) != 0;
+      if (want2) {
+        h->tma2 = tma2_plan_create(g, h->d, err, sizeof(err));
+        if (h->tma2) h->nslots = std::max(h->nslots, tma2_plan_blocks(h->tma2));
+      }
     } else if (env && !strcmp(env, "tma")) {
       return cleanup(Fail(APHCG_ERR_CUDA, "TMA kernel requested but unavailable: %s", err));
     }
@@ -652,6 +663,7 @@ int aphcg_destroy(aphcg_t* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   InvalidateGraphs(h);
   if (h->tma) tma_plan_destroy(h->tma);
+  if (h->tma2) tma2_plan_destroy(h->tma2);
   if (h->comm) Nccl().CommDestroy(h->comm);
   for (int q = 0; q < kMaxRanks; ++q)
     if (h->peer_opened[q]) cudaIpcCloseMemHandle(h->peer[q]);
@@ -1197,7 +1209,9 @@ int aphcg_profile_kernels(aphcg_t* h, int32_t iters, double* ms_dir_spmv, double
   for (auto& e : ev) CK(cudaEventCreate(&e));
   for (int i = 0; i < iters; ++i) {
     CK(cudaEventRecord(ev[3 * i], h->stream));
-    if (h->use_tma) {
+    if (h->use_tma && h->tma2 && h->sym) {
+      launch_dir_spmv_stream(h->tma2, h->g, h->d, true, h->stream);
+    } else if (h->use_tma) {
       launch_dir_spmv_tma(h->tma, h->g, h->d, true, h->sym, h->stream);
     } else {
       launch_dir_spmv_plain(h->g, h->d, h->vx, true, h->stream);
@@ -1237,8 +1251,12 @@ int aphcg_profile_kernels(aphcg_t* h, int32_t iters, double* ms_dir_spmv, double
 
 int aphcg_describe(aphcg_t* h, char* buf, int32_t buflen) {
   if (!h || !buf || buflen < 1) return Fail(APHCG_ERR_ARG, "bad argument");
-  char t[160] = "";
-  if (h->use_tma) tma_plan_describe(h->tma, t, sizeof(t));
+  char t[200] = "";
+  if (h->use_tma && h->tma2 && h->sym) {
+    tma2_plan_describe(h->tma2, t, sizeof(t));
+  } else if (h->use_tma) {
+    tma_plan_describe(h->tma, t, sizeof(t));
+  }
   if (h->persist) {
     snprintf(buf, buflen,
              "loop=persistent-cooperative ctas=%u planes_per_tile=%d update_rows=%d (two grid "
@@ -1247,7 +1265,8 @@ int aphcg_describe(aphcg_t* h, char* buf, int32_t buflen) {
     return 0;
   }
   snprintf(buf, buflen, "spmv=%s%s %s precond=%s graph=%d allreduce=%s", h->use_tma ? "tma" : "plain",
-           h->use_tma ? (h->sym ? "-sym4" : "-gen7") : "", t, h->precond ? "jacobi" : "none",
+           h->use_tma ? (h->sym ? (h->tma2 ? "-stream-sym4" : "-sym4") : "-gen7") : "", t,
+           h->precond ? "jacobi" : "none",
            h->use_graph ? 1 : 0,
            h->single ? "none"
                      : (h->use_mail ? (h->wait_in_kernel ? "peer-mailbox/in-kernel-wait"

@@ -56,6 +56,15 @@ void tma_plan_describe(const TmaPlan* p, char* buf, int buflen);
 // sym: read 4 coefficient streams instead of 7 (matrix verified symmetric)
 void launch_dir_spmv_tma(const TmaPlan* p, const Geom& g, const DevPtrs& d, bool single, bool sym,
                          cudaStream_t s);
+// The same stage with EVERY operand staged in shared memory by TMA (cg_spmv_tma2.cu);
+// symmetric storage only.
+struct Tma2Plan;
+Tma2Plan* tma2_plan_create(const Geom& g, const DevPtrs& d, char* err, int errlen);
+void tma2_plan_destroy(Tma2Plan* p);
+unsigned tma2_plan_blocks(const Tma2Plan* p);
+void tma2_plan_describe(const Tma2Plan* p, char* buf, int buflen);
+void launch_dir_spmv_stream(const Tma2Plan* p, const Geom& g, const DevPtrs& d, bool single,
+                            cudaStream_t s);
 // sets *flag (device int) to 1 if any off-diagonal pair differs: a2[c] != a1[c+1],
 // a4[c] != a3[c+row], a6[c] != a5[c+plane] (inside this slab)
 void launch_check_symmetry(const Geom& g, const DevPtrs& d, int* flag, cudaStream_t s);

@@ -22,6 +22,7 @@
 
 #include "cg_kernels.cuh"
 #include "cg_launch.h"
+#include "cg_tma.cuh"
 
 namespace acg {
 
@@ -53,39 +54,6 @@ struct Cfg {
   static constexpr int kSmemBytes = S * 2 * BOXB + RING * BOXB + S * 8 + 128;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar,
-                                            int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-
 // kSym: the matrix is exactly symmetric (checked at upload), so the coefficient
 // towards the upper neighbour is read as the lower coefficient OF that
 // neighbour: 4 coefficient streams instead of 7 (x+ comes from the next lane by
@@ -94,10 +62,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // L2 prefetch of one row segment (bytes: multiple of 16), no register or
 // shared-memory cost: lets the HBM->L2 stream of the read-once arrays run `pd`
 // planes ahead of the CTA's compute phase.
-__device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 // kDefer (symmetric storage only; OPT-IN via APHCG_DEFER=1, prepared at the end of round 1
 // without GPU access and therefore not the default): everything that merely CONSUMES a freshly
 // loaded coefficient -- the lane shuffle for x+, the y-/z- register aliases -- is moved from the

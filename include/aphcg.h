@@ -56,6 +56,9 @@ enum {
                                 residual and exit rule unchanged (norm of r).  The
                                 reference's SolverConjugate is unpreconditioned, so
                                 iteration counts differ unless diag(A) is constant. */
+  APHCG_NO_STREAM = 1u << 7,  /* symmetric storage: keep the direction kernel whose coefficient
+                                streams go HBM -> registers (k_dir_spmv_tma) instead of the
+                                one that stages every operand in shared memory by TMA */
   APHCG_NO_PERSISTENT = 1u << 6 /* never run the loop as ONE persistent cooperative kernel.
                                 By default a single-GPU solve whose fields fit in L2 (about
                                 100^3 cells and less) does: same arithmetic, two grid-wide

@@ -70,3 +70,33 @@ for rep in sorted(glob.glob(os.path.join(GO, "prof_*.ncu-rep"))):
                     i = hdr.index(m)
                     w.writerow([r[hdr.index("ID")], r[hdr.index("Kernel Name")][:48], m, r[i], units[i]])
     print("wrote", "%s_%s_raw.csv" % (tag, name))
+
+# ---- <tag>_traffic.json: DRAM bytes per launch of the two loop kernels (bench.py's
+# roofline.traffic); usage: summarize_ncu.py <tag> <kernel tag of aphcg_describe> [cells]
+if len(sys.argv) > 2:
+    import json
+    ktag = sys.argv[2]
+    cells = int(sys.argv[3]) if len(sys.argv) > 3 else 512 ** 3
+
+    def dram_bytes(name):
+        path = os.path.join(OUT, "%s_%s_raw.csv" % (tag, name))
+        per = collections.defaultdict(float)
+        for r in csv.DictReader(open(path)):
+            if r["metric"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}[r["unit"]]
+                per[int(r["launch"])] += float(r["value"]) * scale
+        return [per[k] for k in sorted(per)]
+
+    d, u = dram_bytes("dir_spmv"), dram_bytes("update")
+    rec = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full "
+                       "capture summarised in %s_*_raw.csv (two consecutive launches of each kernel: "
+                       "with batched x updates the direction kernel alternates between an 'even' launch "
+                       "that applies two deferred x updates and an 'odd' one that applies none); "
+                       "bench.py reports the mean as roofline.traffic" % tag,
+           "cells": cells,
+           "kernels": {ktag: {"k_dir_spmv_bytes_per_launch": sum(d) / len(d),
+                              "k_dir_spmv_launches": d,
+                              "k_update_bytes_per_launch": sum(u) / len(u)}}}
+    with open(os.path.join(OUT, tag + "_traffic.json"), "w") as f:
+        json.dump(rec, f, indent=1)
+    print("wrote", tag + "_traffic.json", rec["kernels"][ktag]["k_dir_spmv_bytes_per_launch"] / cells, "B/cell")

@@ -39,9 +39,10 @@ def compare_solutions(case, x, xo):
     return rel_max_abs(x, xo)
 
 
-VARIANTS = [pytest.param(0, id="tma+sym+graph"),
+VARIANTS = [pytest.param(0, id="tma-stream+sym+graph"),
             pytest.param(capi.APHCG_NO_SYM, id="tma+7coef+graph"),
             pytest.param(capi.APHCG_NO_TMA, id="plain+graph"),
+            pytest.param(capi.APHCG_NO_STREAM, id="tma-ldg+sym+graph"),
             pytest.param(capi.APHCG_NO_TMA | capi.APHCG_NO_GRAPH, id="plain+nograph"),
             pytest.param(capi.APHCG_NO_GRAPH, id="tma+nograph")]
 
@@ -79,7 +80,7 @@ def rhs_norm_of(case):
     return float(np.sqrt((case["system"][..., 7] ** 2).sum() / __import__('aphros_b200').systems.cell_volume(shape)))
 
 
-@pytest.mark.parametrize("flags", VARIANTS[:3])
+@pytest.mark.parametrize("flags", VARIANTS[:4])
 @pytest.mark.parametrize("name", sorted(PARITY_CASES))
 def test_iterations_to_tolerance(gpu, name, flags):
     """iteration count to a 1e-8 relative residual (the north star's setting,
@@ -100,7 +101,7 @@ def test_iterations_to_tolerance(gpu, name, flags):
     assert info.residual < conf.tol
 
 
-@pytest.mark.parametrize("flags", VARIANTS[:3])
+@pytest.mark.parametrize("flags", VARIANTS[:4])
 @pytest.mark.parametrize("name", sorted(PARITY_CASES))
 def test_solution_parity(gpu, name, flags):
     """solution within 1e-10 relative max-abs of the oracle's once both are
