@@ -628,9 +628,10 @@ int aphcg_create(aphcg_t** out, const aphcg_desc* desc) {
     }
   }
   // Small single-GPU meshes: the whole loop as one persistent cooperative kernel (DESIGN.md
-  // section 3).  Limit: the fields (13 arrays) should stay in the 126 MB L2.
+  // section 3).  Limit: measured crossover with the two-kernel iteration (64^3: 10.3 vs 25.1 us
+  // per iteration; 96^3: 32.8 vs 30.7).
   {
-    int64_t max_cells = 1200000;
+    int64_t max_cells = 700000;
     if (const char* ep = getenv("APHCG_PERSISTENT")) max_cells = atoll(ep) == 1 ? max_cells : atoll(ep);
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ds.device);

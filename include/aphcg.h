@@ -60,8 +60,8 @@ enum {
                                 streams go HBM -> registers (k_dir_spmv_tma) instead of the
                                 one that stages every operand in shared memory by TMA */
   APHCG_NO_PERSISTENT = 1u << 6 /* never run the loop as ONE persistent cooperative kernel.
-                                By default a single-GPU solve whose fields fit in L2 (about
-                                100^3 cells and less) does: same arithmetic, two grid-wide
+                                By default a single-GPU solve of at most 700 000 cells (about
+                                88^3) does: same arithmetic, two grid-wide
                                 barriers per iteration instead of two launches. */
 };
 

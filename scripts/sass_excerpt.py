@@ -38,7 +38,7 @@ with open(out, "w") as f:
     for fn, c in counts.items():
         if c:
             f.write("%-46s %s\n" % (fn, "  ".join("%s x%d" % kv for kv in sorted(c.items()))))
-    key = next(k for k in counts if k.startswith("k_dir_spmv_tma<128, true, true, false>"))
+    key = next(k for k in counts if k.startswith("k_dir_spmv_stream<64, true>"))
     f.write("\n# %s -- the benchmark's direction kernel, in program order\n" % key)
     f.write("\n".join(lines[key]) + "\n")
 print("wrote", out)
