@@ -20,6 +20,7 @@ import numpy as np
 
 __all__ = [
     "projection_rows",
+    "projection_inputs",
     "cell_volume",
     "tlinear_system",
     "density_poisson_system",
@@ -277,3 +278,37 @@ def projection_rows(rho, vx, vy, vz, source=None, dt=1e-3, periodic=(False, Fals
         e7 = e7 - 0.0 * vol
     rows[..., 7] = e7
     return rows
+
+
+def projection_inputs(local_shape, spheres, rho_in=1e-3, rho_out=1.0, z0=0, nz_global=None):
+    """What a caller of aphcg_assemble_projection holds for the S2..S4 bubble systems (walls on
+    all sides): the cell density of a z-slab WITH its two ghost planes, and the face volume
+    fluxes of density_poisson_system's velocity field.  Returns (rho (nzl+2,ny,nx),
+    vx (nzl,ny,nx+1), vy (nzl,ny+1,nx), vz (nzl+1,ny,nx)); the caller may pass preallocated
+    (e.g. pinned) arrays through `out=(rho, vx, vy, vz)`."""
+    nzl, ny, nx = local_shape
+    nzg = nz_global if nz_global is not None else nzl
+    h = 1.0 / max(nx, ny, nzg)
+    # planes z0-1 .. z0+nzl; outside the domain: a copy of the boundary plane (any finite
+    # value does: the wall coefficient is zero)
+    lo, hi = max(z0 - 1, 0), min(z0 + nzl + 1, nzg)
+    core = sphere_density((hi - lo, ny, nx), spheres, rho_out, rho_in, z0=lo, nz_global=nzg)
+    rho = np.concatenate(([core[:1]] if z0 == 0 else []) + [core]
+                         + ([core[-1:]] if z0 + nzl == nzg else []))
+    xc, yc = _centres(nx, h), _centres(ny, h)
+    zc = (np.arange(nzl, dtype=np.float64) + z0 + 0.5) * h
+    xf = np.arange(nx + 1, dtype=np.float64) * h
+    yf = np.arange(ny + 1, dtype=np.float64) * h
+    zf = (np.arange(nzl + 1, dtype=np.float64) + z0) * h
+    hh = h * h
+    sx, sy, sz = np.sin(np.pi * xf), np.sin(np.pi * yf), np.sin(np.pi * zf)
+    sx[0] = sx[-1] = 0.0            # no flux through the walls
+    sy[0] = sy[-1] = 0.0
+    if z0 == 0:
+        sz[0] = 0.0
+    if z0 + nzl == nzg:
+        sz[-1] = 0.0
+    vx = np.broadcast_to(((sx[None, :] * np.cos(2 * np.pi * yc)[:, None]) * hh)[None], (nzl, ny, nx + 1))
+    vy = np.broadcast_to(((sy[None, :] * np.cos(2 * np.pi * zc)[:, None]) * hh)[:, :, None], (nzl, ny + 1, nx))
+    vz = np.broadcast_to(((sz[:, None] * np.cos(2 * np.pi * xc)[None, :]) * hh)[:, None, :], (nzl + 1, ny, nx))
+    return rho, vx, vy, vz

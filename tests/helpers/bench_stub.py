@@ -49,6 +49,7 @@ class StubSolver:
     TimerStop = lambda self: 1290.0
     ProfileKernels = lambda self, n: (1.89, 0.525)
     AssembleSpheres = UploadGuess = TimerStart = SetConf = close = lambda self, *a, **k: None
+    AssembleProjection = DownloadSolution = lambda self, *a, **k: None
 
 
 aphros_b200.SolverConjugateCuda = StubSolver
@@ -65,6 +66,8 @@ bench.strong_measurement = lambda args, world, rank, local_rank, d, barrier: {
     "value": 9.0e10, "unit": bench.UNIT, "n1_value": 5.2e10, "efficiency_vs_n1": 9.0 / (world * 5.2)}
 capi.PinnedArray = type("PA", (), {"__init__": lambda self, shape: setattr(self, "array", np.zeros(2)),
                                    "free": lambda self: None})
+from aphros_b200 import systems  # noqa: E402
+systems.projection_inputs = lambda *a, **k: tuple(np.zeros(2) for _ in range(4))
 capi.lib = lambda: types.SimpleNamespace(aphcg_download_system=lambda *a: 0)
 capi.ptr = lambda a: None
 sys.argv = ["bench.py", "--gpus", str(world), "--steps", "2", "--warmup", "1"]

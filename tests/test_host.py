@@ -89,6 +89,7 @@ def test_bench_line_contract_with_stubbed_solver(world):
     assert line["n_gpus"] == world and line["dtype"] == "f64" and line["vs_baseline"] is None
     assert "workload" in line["config"] and "model" not in line["config"]
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e_projection"])
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
     assert {"rel_max_abs", "iter", "iter_reference", "ok"} <= set(line["parity"])
@@ -246,3 +247,18 @@ def test_two_rank_plumbing_gloo(built, tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, "rank %d failed:\n%s" % (r, o)
         assert "rank %d ok" % r in o
+
+
+def test_bench_host_helpers():
+    """bench.py's host-side guards: the memory figure honours cgroup limits, the scratch
+    directory has room, NUMA binding is a no-op where the topology cannot be read"""
+    sys.path.insert(0, ROOT)
+    import bench
+    from aphros_b200 import distr
+    gb = bench.host_ram_gb()
+    assert 0.0 < gb < 1e5
+    assert bench.scratch_dir(1) is not None
+    assert bench.scratch_dir(10 ** 18) is None
+    before = os.sched_getaffinity(0)
+    assert distr.bind_to_gpu_numa_node(0) is None or isinstance(distr.bind_to_gpu_numa_node(0), str)
+    os.sched_setaffinity(0, before)
