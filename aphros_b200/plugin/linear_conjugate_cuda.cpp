@@ -411,6 +411,7 @@ class ModuleLinearConjugateCuda : public ModuleLinear<M> {
     if (!var.Int(key("cuda_graph"), 1)) flags |= APHCG_NO_GRAPH;
     if (!var.Int(key("cuda_tma"), 1)) flags |= APHCG_NO_TMA;
     if (!var.Int(key("cuda_persistent"), 1)) flags |= APHCG_NO_PERSISTENT;
+    if (!var.Int(key("cuda_stream"), 1)) flags |= APHCG_NO_STREAM;
     // opt-in diagonal preconditioner (NOT SolverConjugate's recurrence; default off)
     if (var.Int(key("jacobi"), 0)) flags |= APHCG_JACOBI_PRECOND;
     return std::make_unique<SolverCuda<M>>(

@@ -499,6 +499,10 @@ class ModuleLinearConjugateCuda(ModuleLinear):
             flags |= capi.APHCG_NO_GRAPH
         if int(var.get("linsolver_" + prefix + "_cuda_tma", 1)) == 0:
             flags |= capi.APHCG_NO_TMA
+        if int(var.get("linsolver_" + prefix + "_cuda_persistent", 1)) == 0:
+            flags |= capi.APHCG_NO_PERSISTENT
+        if int(var.get("linsolver_" + prefix + "_cuda_stream", 1)) == 0:
+            flags |= capi.APHCG_NO_STREAM
         ndev = int(var.get("cuda_devices", 1))
         per_dev = int(var.get("cuda_slabs_per_device", 1))
         if ndev * per_dev > 1:  # one process, several z-slabs: devices cuda_device..+ndev-1
