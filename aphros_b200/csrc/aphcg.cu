@@ -443,12 +443,24 @@ int EnsureHistory(aphcg_t* h, int maxiter) {
 // Replays iterations until the device-side exit rule fires.
 // The persistent kernel stops by itself; the host only bounds a launch (so that a
 // tolerance-driven solve is looked at now and then) and repeats until the exit flag is set.
+int RunLoop(aphcg_t* h, bool jacobi, const aphcg_conf* conf);
+
 int RunLoopPersistent(aphcg_t* h, const aphcg_conf* conf) {
   const long limit = std::max<long>((long)conf->maxiter + 1, (long)conf->miniter);
   long enq = 0;
   for (;;) {
     const int n = (int)std::min<long>(limit - enq > 0 ? limit - enq : 1, 4096);
-    CK(launch_cg_persistent(h->g, h->d, h->vx, h->pplan, n, h->stream));
+    const cudaError_t le = launch_cg_persistent(h->g, h->d, h->vx, h->pplan, n, h->stream);
+    if (le != cudaSuccess && enq == 0) {
+      // the cooperative launch was refused (co-residency not available in this context, e.g.
+      // under MPS limits): nothing has run yet, so take the two-kernel iteration for this
+      // handle from now on.  The state already says "no batched x update", which those
+      // kernels honour.
+      cudaGetLastError();
+      h->persist = false;
+      return RunLoop(h, false, conf);
+    }
+    CK(le);
     h->launches++;
     enq += n;
     CK(cudaMemcpyAsync(h->h_st, h->st, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
