@@ -146,6 +146,29 @@ __global__ void __launch_bounds__(Cfg2<TXT>::NT, Cfg2<TXT>::MINB)
   const int ob = (ly + 1) * BW + 2 + 2 * lx;  // own pair inside a box
   const int ot = ly * TX + 2 * lx;            // own pair inside a tile
 
+  // The pairs of the (TX+4) x (TY+2) box this thread turns into p_new every plane, and what it
+  // stores of them (interior + the face ghost cells of boundary tiles): the same for every
+  // plane, so the index arithmetic is done once.  mode: -1 no pair, 0 compute only,
+  // 1 first cell, 2 second cell, 3 both.
+  constexpr int kPairs = (BOX / 2 + NT - 1) / NT;
+  int pn_mode[kPairs];
+  int64_t pn_off[kPairs];
+#pragma unroll
+  for (int k = 0; k < kPairs; ++k) {
+    const int e = tid + k * NT;
+    pn_mode[k] = -1;
+    pn_off[k] = 0;
+    if (e < BOX / 2) {
+      const int row = e / (BW / 2), cp = e - row * (BW / 2);
+      const int y = y0 - 1 + row, x = x0 - 2 + 2 * cp;
+      const bool iny = (y >= own_ylo && y < own_yhi);
+      const bool in0 = iny && (x >= own_xlo && x < own_xhi);
+      const bool in1 = iny && (x + 1 >= own_xlo && x + 1 < own_xhi);
+      pn_mode[k] = (in0 ? 1 : 0) | (in1 ? 2 : 0);
+      pn_off[k] = g.poff + x + (int64_t)y * g.py;
+    }
+  }
+
   double acc = 0.0;
   Vec<2> zcarry;
   zcarry.v[0] = zcarry.v[1] = 0.0;
@@ -192,31 +215,28 @@ __global__ void __launch_bounds__(Cfg2<TXT>::NT, Cfg2<TXT>::MINB)
 
     // -- (a) p_new = r + beta*p_old on the whole box; store what this CTA owns --------
     const bool z_owned = z_inner || (z == -1 && k0 == 0) || (z == g.nzl && k1 == g.nzl);
-    for (int e = tid; e < BOX / 2; e += NT) {
-      const double2 rv = *reinterpret_cast<const double2*>(sr + 2 * e);
-      const double2 pv = *reinterpret_cast<const double2*>(sp + 2 * e);
+#pragma unroll
+    for (int k = 0; k < kPairs; ++k) {
+      if (pn_mode[k] < 0) continue;  // no such pair for this thread
+      const int e2 = 2 * (tid + k * NT);
+      const double2 rv = *reinterpret_cast<const double2*>(sr + e2);
+      const double2 pv = *reinterpret_cast<const double2*>(sp + e2);
       double2 o;
       o.x = fma(beta, pv.x, rv.x);  // linear.ipp:97-99
       o.y = fma(beta, pv.y, rv.y);
-      *reinterpret_cast<double2*>(rg + 2 * e) = o;
-      if (z_owned) {
-        const int row = e / (BW / 2), cp = e - row * (BW / 2);
-        const int y = y0 - 1 + row, x = x0 - 2 + 2 * cp;
-        if (y >= own_ylo && y < own_yhi) {
-          const bool in0 = (x >= own_xlo && x < own_xhi);
-          const bool in1 = (x + 1 >= own_xlo && x + 1 < own_xhi);
-          double* dst = pn_glob + g.poff + x + (int64_t)y * g.py + (int64_t)z * g.pz;
-          if (in0 && in1) {
-            if (pstream) {
-              __stcs(reinterpret_cast<double2*>(dst), o);
-            } else {
-              *reinterpret_cast<double2*>(dst) = o;
-            }
-          } else if (in0) {
-            dst[0] = o.x;
-          } else if (in1) {
-            dst[1] = o.y;
+      *reinterpret_cast<double2*>(rg + e2) = o;
+      if (z_owned && pn_mode[k] > 0) {
+        double* dst = pn_glob + pn_off[k] + (int64_t)z * g.pz;
+        if (pn_mode[k] == 3) {
+          if (pstream) {
+            __stcs(reinterpret_cast<double2*>(dst), o);
+          } else {
+            *reinterpret_cast<double2*>(dst) = o;
           }
+        } else if (pn_mode[k] == 1) {
+          dst[0] = o.x;
+        } else {
+          dst[1] = o.y;
         }
       }
     }
