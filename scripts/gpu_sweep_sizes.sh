@@ -7,7 +7,7 @@ out=gpurun_out/sweep_sizes.jsonl
 : > $out
 sizes=${@:-128 192 256 384 512 768 1024}
 for n in $sizes; do
-  timeout 600 python bench.py --size $n --steps 3 --warmup 3 --no-e2e --no-cpu >> $out 2>> gpurun_out/sweep_sizes.err
+  timeout 600 python bench.py --size $n --steps 3 --warmup 3 --no-e2e --no-cpu --no-parity >> $out 2>> gpurun_out/sweep_sizes.err
 done
 python - <<'PY'
 import json
